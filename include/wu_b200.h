@@ -1,0 +1,146 @@
+/* wu_b200.h — C ABI of libwu_b200.so: the sm_100a kernels behind the cUNet generator hot path.
+ *
+ * The reference (Sota0726/weather-Unet) has no FFI: its generator is Python calling ATen/cuDNN.
+ * Each entry point below therefore names the reference call site(s) (file:line in the reference
+ * tree) whose arithmetic it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never allocates
+ *     persistent memory and never frees caller memory; scratch comes in through `workspace`;
+ *   - activations are NHWC bf16 ([B][H][W][C], C contiguous) unless stated; parameters and
+ *     parameter gradients are fp32 in the reference's own layouts (state_dict shapes);
+ *   - every call is asynchronous on `stream` (a cudaStream_t), re-entrant, and keeps no mutable
+ *     global state; returns WU_OK or an error code, message via wu_last_error() (thread-local);
+ *   - no CPU fallback exists: a non-sm_100 device is an error.
+ */
+#ifndef WU_B200_H_
+#define WU_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WU_OK 0
+#define WU_ERR_INVALID 1     /* bad shape / argument */
+#define WU_ERR_CUDA 2        /* CUDA runtime / driver error */
+#define WU_ERR_UNSUPPORTED 3 /* device is not sm_100 */
+
+typedef void* wu_stream_t; /* cudaStream_t */
+
+const char* wu_last_error(void);
+int wu_version(void);
+/* 0 when the current device can run the kernels (compute capability 10.x). */
+int wu_device_check(void);
+
+/* ---- weights ---------------------------------------------------------------------------------
+ * nn.Conv2d(cin, cout, 3, padding=1).weight (nets.py:20,22) fp32 [cout][cin][3][3]  ->
+ *   w_fprop bf16 [cout][9*cin]  with k = (r*3+s)*cin + ci           (B operand of fprop)
+ *   w_dgrad bf16 [cin][9*cout]  with k = ((2-r)*3+(2-s))*cout + co  (B operand of dgrad; may be NULL)
+ */
+int wu_pack_conv3x3_weights(const float* w, int cout, int cin, void* w_fprop, void* w_dgrad,
+                            wu_stream_t stream);
+
+/* ---- 3x3 / stride 1 / pad 1 convolution as tcgen05 implicit GEMM ------------------------------
+ * Replaces nn.Conv2d(…,3,padding=1) + nn.ReLU (nets.py:18-24) and, with src1 != NULL, the
+ * torch.cat([x, skip], 1) feeding it (cunet.py:62,69,76): the K loop walks src0's c0 channels and
+ * then src1's c1 channels, so the concatenated tensor is never materialised.
+ *   dst[b,h,w,co] = act( bias[co] + sum_{r,s,ci} src[b,h+r-1,w+s-1,ci] * w_packed[co][(r*3+s)*C+ci] )
+ * then, if relu_mask_src != NULL (same shape as dst), dst = relu_mask_src > 0 ? dst : 0.
+ * The same entry point is the data-gradient pass (autograd of nets.py:20,22): call it with
+ * src0 = dY, w_packed = w_dgrad, bias = NULL, relu = 0 and relu_mask_src = the forward output of
+ * the layer below (its ReLU mask).  c0, c1, cout must be multiples of 64; bias may be NULL.
+ */
+int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
+                     const float* bias, int relu, const void* relu_mask_src, void* dst, int cout,
+                     int B, int H, int W, wu_stream_t stream);
+
+/* Weight + bias gradient of the same convolution (autograd of nets.py:20,22):
+ *   dw[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * src[b,h+r-1,w+s-1,ci]     (fp32, overwritten)
+ *   db[co]           = sum_{b,h,w} dy[b,h,w,co]                              (fp32, may be NULL)
+ * src is the two-source concatenation as in fprop.  Split-K partials live in `workspace`
+ * (wu_conv3x3_wgrad_workspace_bytes); the result is deterministic for a fixed shape.
+ */
+size_t wu_conv3x3_wgrad_workspace_bytes(int cin_total, int cout, int B, int H, int W);
+int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int c1, const void* dy, int cout,
+                     int B, int H, int W, float* dw, float* db, void* workspace,
+                     size_t workspace_bytes, wu_stream_t stream);
+
+/* ---- first layer: Conv2d(3,64,3,padding=1)+ReLU on the NCHW fp32 image (cunet.py:21,45) -------
+ * x fp32 NCHW [B][3][H][W]; w fp32 [64][3][3][3]; dst NHWC bf16 [B][H][W][64].  HBM/FMA bound
+ * (K = 27), so it is a direct convolution, not a tensor-core GEMM. */
+int wu_conv_first_fprop(const float* x, const float* w, const float* bias, void* dst, int B, int H,
+                        int W, wu_stream_t stream);
+/* dy NHWC bf16 [B][H][W][64] (already ReLU-masked) -> dw fp32 [64][3][3][3], db fp32 [64]. */
+size_t wu_conv_first_wgrad_workspace_bytes(int B, int H, int W);
+int wu_conv_first_wgrad(const float* x, const void* dy, float* dw, float* db, int B, int H, int W,
+                        void* workspace, size_t workspace_bytes, wu_stream_t stream);
+
+/* ---- last layer: Conv2d(64,3,1) + Tanh (cunet.py:39-40,80-82) ---------------------------------
+ * x NHWC bf16 [B][H][W][64]; w fp32 [3][64]; y fp32 NCHW [B][3][H][W]. */
+int wu_conv_last_tanh_fprop(const void* x, const float* w, const float* bias, float* y, int B,
+                            int H, int W, wu_stream_t stream);
+/* gy, y fp32 NCHW.  gx NHWC bf16 = relu'(x) * (W^T (gy * (1 - y^2)));  dw [3][64], db [3] fp32. */
+size_t wu_conv_last_tanh_bprop_workspace_bytes(int B, int H, int W);
+int wu_conv_last_tanh_bprop(const float* gy, const float* y, const void* x, const float* w,
+                            void* gx, float* dw, float* db, int B, int H, int W, void* workspace,
+                            size_t workspace_bytes, wu_stream_t stream);
+
+/* ---- nn.MaxPool2d(2) (cunet.py:27,46,49,52) ---------------------------------------------------
+ * src NHWC bf16 [B][H][W][C] -> dst [B][H/2][W/2][C]; C % 8 == 0, H and W even. */
+int wu_maxpool2_fwd(const void* src, void* dst, int B, int H, int W, int C, wu_stream_t stream);
+/* Gradient arriving at a skip tensor `y` (post-ReLU conv output): the pooled branch routes
+ * g_pool to the first maximum of each 2x2 window (PyTorch tie rule), the decoder's skip branch
+ * adds g_skip (may be NULL), and the ReLU mask of y is applied:
+ *   g[b,h,w,c] = y > 0 ? g_skip + (argmax ? g_pool[b,h/2,w/2,c] : 0) : 0 */
+int wu_maxpool2_bwd(const void* y, const void* g_pool, const void* g_skip, void* g, int B, int H,
+                    int W, int C, wu_stream_t stream);
+
+/* ---- AdaIN (utils.py:26-51) fused with Upsample(x2, bilinear, align_corners) + Dropout --------
+ * Step 1: per-(b,c) partial sums of x and x^2 over H*W (utils.py:36-38).
+ *   partial fp32 [B][nchunk][C][2], nchunk = wu_adain_stats_chunks(H*W). */
+int wu_adain_stats_chunks(int HW);
+int wu_adain_stats(const void* x, float* partial, int B, int HW, int C, wu_stream_t stream);
+/* Step 2: style = l1(cond) (utils.py:46) -> y_mean / y_std over the 4 style numbers per channel,
+ * combined with the instance statistics into an affine map (all fp32, [B][C]):
+ *   mean, rstd = 1/sqrt(var_unbiased + eps), ystd, scale = ystd*rstd, shift = ymean - mean*scale.
+ * cond fp32 [B][nc]; lw fp32 [4C][nc]; lb fp32 [4C]. */
+int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, const float* partial,
+                       float* mean, float* rstd, float* ystd, float* scale, float* shift, int B,
+                       int C, int nc, int HW, float eps, wu_stream_t stream);
+/* Step 3 (cunet.py:59-61): u[b,Y,X,c] = keep * bilinear_x2(x*scale+shift)[b,Y,X,c] / (1-p).
+ * Dropout: p_drop == 0 -> none; else if mask != NULL it is a uint8 NHWC [B][2h][2w][C] keep mask;
+ * else keep bits come from a Philox4x32-10 stream keyed by (seed, element index). */
+int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u, int B,
+                         int h, int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
+                         wu_stream_t stream);
+/* Backward, step 1: gz = adjoint(dropout o upsample)(gu) at low resolution, plus per-(b,c)
+ * partial sums S1 = sum gz, S2 = sum gz * xhat (xhat = (x-mean)*rstd).
+ *   gz bf16 [B][h][w][C]; partial fp32 [B][nchunk][C][2], nchunk = wu_adain_stats_chunks(h*w). */
+int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean, const float* rstd,
+                         void* gz, float* partial, int B, int h, int w, int C, float p_drop,
+                         uint64_t seed, const uint8_t* mask, wu_stream_t stream);
+/* Backward, step 2: reduce the partials, emit k1 = S1/N and k2 = S2/(N-1) ([B][C] fp32) and the
+ * gradients of l1.weight / l1.bias (utils.py:31,46), overwritten: dlw [4C][nc], dlb [4C].
+ * gh is caller scratch, fp32 [B][4C] (gradient of the style vector l1(cond)). */
+int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb, const float* partial,
+                       const float* ystd, float* k1, float* k2, float* gh, float* dlw, float* dlb,
+                       int B, int C, int nc, int HW, wu_stream_t stream);
+/* Backward, step 3: gx = relu'(x) * rstd*ystd * (gz - k1 - xhat*k2), bf16 [B][h][w][C]. */
+int wu_adain_bwd_apply(const void* gz, const void* x, const float* mean, const float* rstd,
+                       const float* ystd, const float* k1, const float* k2, void* gx, int B,
+                       int HW, int C, wu_stream_t stream);
+
+/* ---- layout helpers (tests, interop with NCHW fp32 PyTorch tensors) ---------------------------*/
+int wu_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W,
+                             wu_stream_t stream);
+int wu_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W,
+                             wu_stream_t stream);
+
+/* Number of kernels this library has launched in the calling process (all threads). */
+unsigned long long wu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WU_B200_H_ */

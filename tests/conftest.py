@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """The in-tree shared library (built by __graft_entry__.build(); never rebuilt on the GPU box
+    unless missing)."""
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB):
+        g.build()
+    from weather_unet_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope="session")
+def cuda(built_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")

@@ -1,0 +1,111 @@
+"""CPU-side checks (no GPU): the oracle against the golden fixture made from the live reference,
+the state_dict contract, the drop-in import surface, and that the C-ABI library loads and exports
+every symbol include/wu_b200.h declares."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "cunet_b2_h32_seed0.npz")
+
+
+def seeded_sd(nc=5, seed=0):
+    from weather_unet_b200 import Conditional_UNet
+    torch.manual_seed(seed)
+    return Conditional_UNet(nc).state_dict()
+
+
+def test_oracle_matches_reference_golden():
+    from oracle import cunet_oracle as orc
+    z = np.load(GOLD)
+    sd = seeded_sd()
+    x, gy = torch.from_numpy(z["x"]), torch.from_numpy(z["gy"])
+    masks = []
+    for i in (3, 2, 1):
+        shape = tuple(int(v) for v in z[f"mask{i}_shape"])
+        bits = np.unpackbits(z[f"mask{i}_bits"])[:int(np.prod(shape))]
+        masks.append(torch.from_numpy(bits.reshape(shape).astype(np.uint8)))
+    for tag in ("hot", "soft"):
+        c = torch.from_numpy(z[f"c_{tag}"])
+        y = orc.forward(sd, x, c, train=False)
+        assert torch.allclose(y, torch.from_numpy(z[f"y_eval_{tag}"]), atol=1e-6, rtol=0)
+        y, grads = orc.forward_backward(sd, x, c, tuple(masks), gy)
+        assert torch.allclose(y, torch.from_numpy(z[f"y_train_{tag}"]), atol=1e-6, rtol=0)
+        assert len(grads) == 36
+        for name, g in grads.items():
+            ref = float(z[f"grad_{tag}_{name}_norm"][0])
+            assert abs(g.norm().item() - ref) <= 1e-4 * ref
+            assert torch.allclose(g.flatten()[:64], torch.from_numpy(z[f"grad_{tag}_{name}_head"]),
+                                  atol=1e-5 * max(1.0, ref), rtol=1e-4)
+
+
+def test_state_dict_contract():
+    sd = seeded_sd()
+    keys = list(sd.keys())
+    assert len(keys) == 39
+    assert sum(v.numel() for v in sd.values()) == 7804622
+    assert keys[0] == "dconv_down1.0.weight" and keys[-1] == "conv_last.bias"
+    for a, C in (("adain3", 512), ("adain2", 256), ("adain1", 128)):
+        assert sd[f"{a}.l1.weight"].shape == (4 * C, 5)
+        assert sd[f"{a}.emb.weight"].shape == (5, 5)  # unused by forward, part of the contract
+    assert sd["dconv_up3.0.weight"].shape == (256, 768, 3, 3)
+    assert sd["conv_last.weight"].shape == (3, 64, 1, 1)
+    z = np.load(GOLD)
+    chk = np.array([[v.double().sum().item(), v.double().abs().sum().item()] for v in sd.values()])
+    assert np.allclose(chk, z["sd_checksum"], rtol=1e-12)
+
+
+def test_dropin_import_surface():
+    import weather_unet_b200.cunet as cunet
+    import weather_unet_b200.nets as nets
+    import weather_unet_b200.ops as ops
+    import weather_unet_b200.utils as utils
+    import weather_unet_b200.disc as disc
+    for n in ("Conditional_UNet",):
+        assert hasattr(cunet, n)
+    for n in ("upsample_box", "double_conv", "r_double_conv", "sn_double_conv"):
+        assert hasattr(nets, n)
+    for n in ("ConditionalNorm", "AdaIN", "BatchNorm", "MakeOneHot", "HalfDropout", "Denormalize"):
+        assert hasattr(utils, n)
+    for n in ("soft_transform", "adv_loss", "l1_loss", "feat_loss", "pred_loss", "dis_hinge",
+              "gen_hinge", "vector_to_one_hot", "get_rand_labels", "get_sequential_labels",
+              "Variable_Float", "make_table_img", "F", "np", "torch", "nn", "Variable"):
+        assert hasattr(ops, n)
+    d = disc.SNDisc(5)
+    assert "conv1.0.weight_orig" in d.state_dict() and "embed.weight_u" in d.state_dict()
+    out = d(torch.randn(2, 3, 32, 32), torch.eye(5)[:2])
+    assert len(out) == 5 and out[0].shape == (2, 1)
+
+
+def test_losses_match_definitions():
+    import weather_unet_b200.ops as ops
+    a, b = torch.randn(4, 1), torch.randn(4, 1)
+    assert torch.allclose(ops.dis_hinge(a, b), torch.relu(1 - b).mean() + torch.relu(1 + a).mean())
+    assert torch.allclose(ops.gen_hinge(a), -a.mean())
+    v = torch.tensor([0.1, 0.7, 0.2])
+    assert torch.equal(ops.vector_to_one_hot(v), torch.tensor([0., 1., 0.]))
+    with pytest.raises(AssertionError):
+        ops.l1_loss(torch.zeros(2), torch.zeros(3))
+
+
+def test_no_cpu_fallback():
+    from weather_unet_b200 import Conditional_UNet
+    from weather_unet_b200._lib import WuError
+    net = Conditional_UNet(5)
+    with pytest.raises(WuError, match="no CPU fallback"):
+        net(torch.zeros(1, 3, 32, 32), torch.zeros(1, 5))
+
+
+def test_library_exports_header_symbols(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "wu_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(wu_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = built_lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/wu_b200.h but not exported"
+    assert declared == set(built_lib.exported_symbols()), declared ^ set(built_lib.exported_symbols())
+    assert lib.wu_version() >= 100

@@ -1,0 +1,134 @@
+"""End-to-end parity of Conditional_UNet on the GPU: against the committed golden fixture (made
+from the live reference by oracle/pin_against_reference.py) and against the oracle run in fp32 on
+the same device.  Tolerances are SURVEY §8c's: bf16 kernels vs fp32 oracle — output max-abs
+<= 3e-2 (range +-1), parameter-gradient rel-L2 <= 3e-2 (5e-2 for the tiny bias vectors) and
+cosine >= 0.999."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "cunet_b2_h32_seed0.npz")
+
+
+def make_net(nc=5, seed=0):
+    from weather_unet_b200 import Conditional_UNet
+    torch.manual_seed(seed)
+    return Conditional_UNet(nc)  # CPU init: identical to the reference under the same seed
+
+
+def golden_masks(z, dev):
+    out = []
+    for i in (3, 2, 1):
+        shape = tuple(int(v) for v in z[f"mask{i}_shape"])
+        bits = np.unpackbits(z[f"mask{i}_bits"])[:int(np.prod(shape))]
+        out.append(torch.from_numpy(bits.reshape(shape).astype(np.uint8)).to(dev))
+    return tuple(out)
+
+
+def test_golden_eval_and_train(cuda):
+    z = np.load(GOLD)
+    net = make_net()
+    chk = np.array([[v.double().sum().item(), v.double().abs().sum().item()]
+                    for v in net.state_dict().values() if v.is_floating_point()])
+    assert np.allclose(chk, z["sd_checksum"], rtol=1e-12), "seeded init differs from the fixture"
+    net = net.to(cuda)
+    x = torch.from_numpy(z["x"]).to(cuda)
+    gy = torch.from_numpy(z["gy"]).to(cuda)
+    net.eval()
+    with torch.no_grad():
+        for tag in ("hot", "soft"):
+            y = net(x, torch.from_numpy(z[f"c_{tag}"]).to(cuda))
+            err = (y.cpu() - torch.from_numpy(z[f"y_eval_{tag}"])).abs().max().item()
+            assert err < 3e-2, f"eval {tag}: max-abs {err}"
+    net.train()
+    masks = golden_masks(z, cuda)
+    for tag in ("hot", "soft"):
+        net.zero_grad()
+        y = net(x, torch.from_numpy(z[f"c_{tag}"]).to(cuda), dropout_masks=masks)
+        err = (y.detach().cpu() - torch.from_numpy(z[f"y_train_{tag}"])).abs().max().item()
+        assert err < 3e-2, f"train {tag}: max-abs {err}"
+        (y * gy).sum().backward()
+        for name, p in net.named_parameters():
+            if name.endswith("emb.weight"):
+                assert p.grad is None
+                continue
+            gn = p.grad.float().norm().item()
+            ref = float(z[f"grad_{tag}_{name}_norm"][0])
+            assert abs(gn - ref) / ref < 5e-2, f"{name}: |g| {gn} vs {ref}"
+            head = torch.from_numpy(z[f"grad_{tag}_{name}_head"])
+            mine = p.grad.float().flatten()[:64].cpu()
+            tol = 8e-2 * head.abs().max().item() + 1e-6
+            assert (mine - head).abs().max().item() < tol, name
+
+
+@pytest.mark.parametrize("B,H,W,nc,train", [(2, 64, 64, 5, True), (1, 32, 96, 6, True),
+                                            (3, 64, 32, 5, False)])
+def test_against_oracle(cuda, B, H, W, nc, train):
+    from oracle import cunet_oracle as orc
+    net = make_net(nc, seed=3).to(cuda)
+    net.train(train)
+    g = torch.Generator().manual_seed(B + H)
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(cuda)
+    c = torch.randn(B, nc, generator=g).to(cuda)
+    gy = torch.randn(B, 3, H, W, generator=g).to(cuda)
+    masks = orc.make_dropout_masks(B, H, W, seed=5, device=cuda) if train else None
+    acts = {}
+    y = net(x, c, dropout_masks=masks, _keep_acts=acts)
+    (y * gy).sum().backward()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    col = {}
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    y_ref = orc.forward(leaf, x, c, train=train, masks=masks, collect=col)
+    (y_ref * gy).sum().backward()
+    for k in ("conv1", "conv2", "conv3", "x4", "up3b", "up2b", "up1b"):
+        a = acts[k].float().permute(0, 3, 1, 2)
+        r = col[k]
+        assert ((a - r).norm() / r.norm()).item() < 1e-2, f"activation {k}"
+    assert (y.detach() - y_ref.detach()).abs().max().item() < 3e-2
+    for name, p in net.named_parameters():
+        if name.endswith("emb.weight"):
+            assert p.grad is None
+            continue
+        gm, gr = p.grad.float().flatten(), leaf[name].grad.flatten()
+        r = ((gm - gr).norm() / gr.norm()).item()
+        cos = torch.nn.functional.cosine_similarity(gm, gr, dim=0).item()
+        lim = 5e-2 if name.endswith("bias") else 3e-2
+        assert r < lim and cos > 0.999, f"{name}: rel-L2 {r:.3e} cos {cos:.5f}"
+
+
+def test_module_surface(cuda):
+    """Same behaviours the reference's callers rely on: strict state_dict round trip, eval/train,
+    no_grad, detach, error on H % 8 != 0 and on batch mismatch, no CPU path."""
+    from weather_unet_b200._lib import WuError
+    net = make_net().to(cuda)
+    assert len(net.state_dict()) == 39
+    assert sum(p.numel() for p in net.parameters()) == 7804622
+    net2 = make_net(seed=9).to(cuda)
+    net2.load_state_dict(net.state_dict(), strict=True)
+    x = torch.rand(2, 3, 32, 32, device=cuda) * 2 - 1
+    c = torch.eye(5, device=cuda)[:2]
+    net.eval(), net2.eval()
+    with torch.no_grad():
+        y1, y2 = net(x, c), net2(x, c)
+    assert torch.equal(y1, y2) and y1.shape == (2, 3, 32, 32) and y1.dtype == torch.float32
+    assert y1.abs().max().item() < 1.0
+    net.train()
+    ya, yb = net(x, c, seed=11), net(x, c, seed=11)
+    assert torch.equal(ya, yb)                      # same seed, same dropout
+    assert not torch.equal(ya, net(x, c, seed=12))  # dropout is live in train mode
+    assert not torch.equal(net(x, c), net(x, c))    # and draws a new seed per call
+    with pytest.raises(RuntimeError):
+        net(torch.rand(1, 3, 244, 244, device=cuda), c[:1])   # demo.py's default size fails too
+    with pytest.raises(AssertionError):
+        net(x, c[:1])
+    with pytest.raises(WuError):
+        make_net()(x.cpu(), c.cpu())
+    # optimiser step changes the master weights -> packed copies refresh
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.0, 0.999), weight_decay=1e-3 / 20)
+    y = net(x, c, seed=1)
+    y.mean().backward()
+    opt.step()
+    assert not torch.equal(net(x, c, seed=1), y)

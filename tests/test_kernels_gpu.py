@@ -1,0 +1,237 @@
+"""Per-kernel parity: every C-ABI entry point against a plain PyTorch fp32 restatement of the same
+reference op (TF32 off), on bf16-representable inputs so the only differences are accumulation
+order and the bf16 rounding of outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def nhwc(t):  # NCHW fp32 -> NHWC bf16
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(t):  # NHWC bf16 -> NCHW fp32
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+CONV_CASES = [
+    # B, H, W, c0, c1, cout
+    (1, 32, 32, 64, 0, 64),
+    (2, 16, 16, 64, 0, 128),
+    (3, 24, 40, 128, 0, 128),
+    (2, 8, 8, 256, 0, 512),
+    (1, 8, 16, 512, 0, 512),
+    (2, 16, 16, 512, 256, 256),
+    (2, 32, 32, 128, 64, 64),
+    (1, 32, 32, 256, 128, 128),
+    (4, 128, 128, 64, 0, 64),
+    (1, 4, 4, 64, 0, 64),
+]
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,cout", CONV_CASES)
+def test_conv3x3_fprop(cuda, B, H, W, c0, c1, cout):
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + H + c0 + cout)
+    cin = c0 + c1
+    x = bf(torch.randn(B, cin, H, W, generator=g)).to(cuda)
+    w = bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(cuda)
+    b = torch.randn(cout, generator=g).to(cuda)
+    wf, wd = K.pack_conv3x3_weights(w)
+    s0 = nhwc(x[:, :c0])
+    s1 = nhwc(x[:, c0:]) if c1 else None
+    y = K.conv3x3(s0, s1, wf, b, True, None, cout)
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    assert rel(nchw(y), ref) < 6e-3
+    # no bias / no relu
+    y2 = K.conv3x3(s0, s1, wf, None, False, None, cout)
+    ref2 = F.conv2d(x, w, None, padding=1)
+    assert rel(nchw(y2), ref2) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,cout", CONV_CASES)
+def test_conv3x3_dgrad(cuda, B, H, W, c0, c1, cout):
+    """Data gradient = the same kernel on dY with the flipped/transposed pack, ReLU mask fused;
+    two-source layers produce the two channel slices with row-sliced weights."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(7 + B + H + c0 + cout)
+    cin = c0 + c1
+    w = bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cout ** 0.5)).to(cuda)
+    dy = bf(torch.randn(B, cout, H, W, generator=g)).to(cuda)
+    below = bf(torch.randn(B, cin, H, W, generator=g)).clamp_min(0).to(cuda)  # post-ReLU input
+    wf, wd = K.pack_conv3x3_weights(w)
+    ref = F.conv_transpose2d(dy, w, padding=1)  # == conv2d input gradient
+    dyh = nhwc(dy)
+    if c1 == 0:
+        gx = K.conv3x3(dyh, None, wd, None, False, nhwc(below), cin)
+        assert rel(nchw(gx), ref * (below > 0)) < 6e-3
+    else:
+        g0 = K.conv3x3(dyh, None, wd[:c0], None, False, None, c0)
+        g1 = K.conv3x3(dyh, None, wd[c0:], None, False, None, c1)
+        assert rel(nchw(g0), ref[:, :c0]) < 6e-3
+        assert rel(nchw(g1), ref[:, c0:]) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,cout", CONV_CASES)
+def test_conv3x3_wgrad(cuda, B, H, W, c0, c1, cout):
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(11 + B + H + c0 + cout)
+    cin = c0 + c1
+    x = bf(torch.randn(B, cin, H, W, generator=g)).to(cuda)
+    dy = bf(torch.randn(B, cout, H, W, generator=g)).to(cuda)
+    s0 = nhwc(x[:, :c0])
+    s1 = nhwc(x[:, c0:]) if c1 else None
+    dw, db = K.conv3x3_wgrad(s0, s1, nhwc(dy))
+    ref_w = torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), dy, padding=1)
+    assert rel(dw, ref_w) < 2e-3
+    assert rel(db, dy.sum(dim=(0, 2, 3))) < 1e-4
+    dw2, _ = K.conv3x3_wgrad(s0, s1, nhwc(dy))
+    assert torch.equal(dw, dw2), "wgrad must be deterministic"
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 24, 40), (3, 64, 64)])
+def test_conv_first(cuda, B, H, W):
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(H)
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(cuda)
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).to(cuda)
+    b = (torch.randn(64, generator=g) * 0.1).to(cuda)
+    y = K.conv_first(x, w, b)
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    assert (nchw(y) - ref).abs().max().item() < 2e-2
+    assert rel(nchw(y), ref) < 4e-3
+    dy = bf(torch.randn(B, 64, H, W, generator=g)).to(cuda)
+    dw, db = K.conv_first_wgrad(x, nhwc(dy))
+    ref_w = torch.nn.grad.conv2d_weight(x, (64, 3, 3, 3), dy, padding=1)
+    assert rel(dw, ref_w) < 1e-4
+    assert rel(db, dy.sum(dim=(0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 24, 40), (3, 64, 64)])
+def test_conv_last_tanh(cuda, B, H, W):
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(H + 1)
+    x = bf(torch.randn(B, 64, H, W, generator=g)).clamp_min(0).to(cuda)
+    w = (torch.randn(3, 64, 1, 1, generator=g) * 0.2).to(cuda)
+    b = (torch.randn(3, generator=g) * 0.1).to(cuda)
+    y = K.conv_last_tanh(nhwc(x), w, b)
+    ref = torch.tanh(F.conv2d(x, w, b))
+    assert (y - ref).abs().max().item() < 1e-5
+    gy = torch.randn(B, 3, H, W, generator=g).to(cuda)
+    gx, dw, db = K.conv_last_tanh_bprop(gy, y, nhwc(x), w)
+    t = gy * (1 - ref * ref)
+    ref_gx = F.conv_transpose2d(t, w) * (x > 0)
+    assert rel(nchw(gx), ref_gx) < 4e-3
+    assert rel(dw, torch.nn.grad.conv2d_weight(x, (3, 64, 1, 1), t)) < 1e-4
+    assert rel(db, t.sum(dim=(0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 8, 24, 256), (3, 16, 16, 128)])
+def test_maxpool(cuda, B, H, W, C):
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(C)
+    x = bf(torch.randn(B, C, H, W, generator=g)).clamp_min(0).to(cuda)
+    y = K.maxpool2(nhwc(x))
+    assert torch.equal(nchw(y), F.max_pool2d(x, 2))
+    g_pool = bf(torch.randn(B, C, H // 2, W // 2, generator=g)).to(cuda)
+    g_skip = bf(torch.randn(B, C, H, W, generator=g)).to(cuda)
+    xr = x.clone().requires_grad_(True)
+    F.max_pool2d(xr, 2).backward(g_pool)
+    ref = (xr.grad + g_skip) * (x > 0)
+    out = K.maxpool2_bwd(nhwc(x), nhwc(g_pool), nhwc(g_skip))
+    assert rel(nchw(out), ref) < 4e-3
+    out2 = K.maxpool2_bwd(nhwc(x), nhwc(g_pool), None)
+    assert rel(nchw(out2), xr.grad * (x > 0)) < 1e-6
+
+
+def _adain_ref(x, c, lw, lb, eps, mask, p):
+    B, C = x.shape[:2]
+    style = F.linear(c, lw, lb).view(B, C, 4)
+    flat = x.reshape(B, C, -1)
+    xs = (flat.var(-1) + eps).sqrt().view(B, C, 1, 1)
+    xm = flat.mean(-1).view(B, C, 1, 1)
+    ys = (style.var(-1) + eps).sqrt().view(B, C, 1, 1)
+    ym = style.mean(-1).view(B, C, 1, 1)
+    z = (x - xm) / xs * ys + ym
+    u = F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=True)
+    if mask is not None:
+        u = u * mask.permute(0, 3, 1, 2).float() / (1 - p)
+    return u
+
+
+@pytest.mark.parametrize("B,h,w,C,nc,p", [(2, 8, 8, 512, 5, 0.3), (3, 16, 24, 128, 5, 0.3),
+                                          (1, 32, 32, 256, 6, 0.0), (2, 4, 4, 128, 5, 0.3)])
+def test_adain_up_drop(cuda, B, h, w, C, nc, p):
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(C + h)
+    x = bf(torch.randn(B, C, h, w, generator=g) * 0.7 + 0.3).clamp_min(0).to(cuda)
+    c = torch.randn(B, nc, generator=g).to(cuda)
+    lw = (torch.randn(4 * C, nc, generator=g) * 0.4).to(cuda)
+    lb = (torch.randn(4 * C, generator=g) * 0.4).to(cuda)
+    mask = (torch.rand(B, 2 * h, 2 * w, C, generator=g) >= p).to(torch.uint8).to(cuda) if p > 0 else None
+    u, st = K.adain_up_drop(nhwc(x), c, lw, lb, 1e-5, p, 0, mask)
+    lwr, lbr = lw.clone().requires_grad_(True), lb.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = _adain_ref(xr, c, lwr, lbr, 1e-5, mask, p)
+    assert rel(nchw(u), ref) < 5e-3
+    flat = x.reshape(B, C, -1)
+    assert rel(st.mean, flat.mean(-1)) < 1e-5
+    assert rel(st.rstd, 1 / (flat.var(-1) + 1e-5).sqrt()) < 1e-4
+    gu = bf(torch.randn(B, C, 2 * h, 2 * w, generator=g)).to(cuda)
+    ref.backward(gu)
+    gx, dlw, dlb = K.adain_up_drop_bwd(nhwc(gu), nhwc(x), c, lw, lb, st)
+    assert rel(nchw(gx), xr.grad * (x > 0)) < 8e-3
+    assert rel(dlw, lwr.grad) < 2e-3
+    assert rel(dlb, lbr.grad) < 2e-3
+
+
+def test_dropout_philox_rate(cuda):
+    """Without an injected mask the keep decisions come from Philox: rate ~ 1-p, scaling 1/(1-p),
+    the same seed reproduces the mask, another seed does not."""
+    from weather_unet_b200 import _ops as K
+    B, h, w, C, nc = 2, 16, 16, 128, 5
+    x = torch.ones(B, h, w, C, dtype=torch.bfloat16, device=cuda)
+    x[:, ::2] = 3.0  # non-constant so the variance is not degenerate
+    c = torch.zeros(B, nc, device=cuda)
+    lw = torch.zeros(4 * C, nc, device=cuda)
+    lb = torch.tensor([0.0, 2.0, 0.0, 2.0], device=cuda).repeat(C)  # y_mean 1, y_std > 0
+    u0, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.0, 5, None)
+    u1, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.3, 5, None)
+    u2, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.3, 5, None)
+    u3, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.3, 6, None)
+    assert torch.equal(u1, u2) and not torch.equal(u1, u3)
+    kept = u1 != 0
+    nz = u0 != 0
+    rate = (kept & nz).sum().item() / nz.sum().item()
+    assert abs(rate - 0.7) < 0.01
+    sel = kept & nz
+    assert rel(u1[sel].float(), u0[sel].float() / 0.7) < 5e-3
+
+
+def test_layout_roundtrip(cuda):
+    from weather_unet_b200 import _ops as K
+    x = bf(torch.randn(2, 70, 9, 13)).to(cuda)
+    y = K.nchw_to_nhwc(x)
+    assert torch.equal(y, nhwc(x))
+    assert torch.equal(K.nhwc_to_nchw(y), x)
+
+
+def test_errors(cuda):
+    from weather_unet_b200 import _ops as K
+    from weather_unet_b200._lib import WuError
+    x = torch.zeros(1, 8, 8, 48, dtype=torch.bfloat16, device=cuda)
+    w = torch.zeros(64, 9 * 48, dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(WuError, match="multiple of 64"):
+        K.conv3x3(x, None, w, None, True, None, 64)
+    with pytest.raises(WuError):
+        K.maxpool2(torch.zeros(1, 7, 8, 64, dtype=torch.bfloat16, device=cuda))

@@ -1,0 +1,207 @@
+"""The cUNet generator (cunet.py:43-82 of the reference) as ONE autograd node over the C ABI.
+
+Forward and backward are explicit kernel schedules: NHWC bf16 activations, fp32 master parameters
+in the reference's state_dict layout, bf16 packed weight copies, fp32 gradients.  The skip
+concatenations (cunet.py:62,69,76) are never materialised: the decoder convolutions walk two
+sources in their K loop, and their data-gradient is produced as two channel slices.
+"""
+import torch
+
+from . import _ops as K
+from ._lib import require_device
+
+# parameter order of the flat argument list of _CUNetFn
+BLOCKS = ("dconv_down1", "dconv_down2", "dconv_down3", "dconv_down4", "dconv_up3", "dconv_up2",
+          "dconv_up1")
+ADAINS = ("adain3", "adain2", "adain1")
+
+
+def param_names():
+    names = []
+    for b in BLOCKS:
+        names += [f"{b}.0.weight", f"{b}.0.bias", f"{b}.2.weight", f"{b}.2.bias"]
+    for a in ADAINS:
+        names += [f"{a}.l1.weight", f"{a}.l1.bias"]
+    names += ["conv_last.weight", "conv_last.bias"]
+    return names
+
+
+PARAM_NAMES = param_names()
+
+
+class PackedWeights:
+    """bf16 K-major copies of the 13 tensor-core convolution weights, refreshed when the fp32
+    master parameter changes (tracked through the tensor version counter)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, name, w):
+        key = (w.data_ptr(), w._version, w.device)
+        hit = self._cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            wf, wd = K.pack_conv3x3_weights(w.detach())
+        self._cache[name] = (key, wf, wd)
+        return wf, wd
+
+    def clear(self):
+        self._cache.clear()
+
+
+class _CUNetFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, c, opts, *params):
+        P = dict(zip(PARAM_NAMES, params))
+        packed = opts["packed"]
+        p_drop = opts["p"] if opts["training"] else 0.0
+        masks = opts.get("masks") or (None, None, None)
+        seed = opts.get("seed", 0)
+        eps = opts["eps"]
+
+        def wf(name):
+            return packed.get(name, P[name])[0]
+
+        def block(src0, src1, name):
+            cout = P[f"{name}.0.weight"].shape[0]
+            a = K.conv3x3(src0, src1, wf(f"{name}.0.weight"), P[f"{name}.0.bias"], True, None, cout)
+            b = K.conv3x3(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], True, None, cout)
+            return a, b
+
+        # encoder (cunet.py:45-54)
+        a1 = K.conv_first(x, P["dconv_down1.0.weight"], P["dconv_down1.0.bias"])
+        conv1 = K.conv3x3(a1, None, wf("dconv_down1.2.weight"), P["dconv_down1.2.bias"], True, None, 64)
+        p1 = K.maxpool2(conv1)
+        d2a, conv2 = block(p1, None, "dconv_down2")
+        p2 = K.maxpool2(conv2)
+        d3a, conv3 = block(p2, None, "dconv_down3")
+        p3 = K.maxpool2(conv3)
+        d4a, x4 = block(p3, None, "dconv_down4")
+        # decoder (cunet.py:59-78)
+        u3, st3 = K.adain_up_drop(x4, c, P["adain3.l1.weight"], P["adain3.l1.bias"], eps[0], p_drop,
+                                  seed, masks[0])
+        up3a, up3b = block(u3, conv3, "dconv_up3")
+        u2, st2 = K.adain_up_drop(up3b, c, P["adain2.l1.weight"], P["adain2.l1.bias"], eps[1], p_drop,
+                                  seed + 1, masks[1])
+        up2a, up2b = block(u2, conv2, "dconv_up2")
+        u1, st1 = K.adain_up_drop(up2b, c, P["adain1.l1.weight"], P["adain1.l1.bias"], eps[2], p_drop,
+                                  seed + 2, masks[2])
+        up1a, up1b = block(u1, conv1, "dconv_up1")
+        y = K.conv_last_tanh(up1b, P["conv_last.weight"], P["conv_last.bias"])
+
+        ctx.acts = dict(x=x, c=c, a1=a1, conv1=conv1, p1=p1, d2a=d2a, conv2=conv2, p2=p2, d3a=d3a,
+                        conv3=conv3, p3=p3, d4a=d4a, x4=x4, u3=u3, up3a=up3a, up3b=up3b, u2=u2,
+                        up2a=up2a, up2b=up2b, u1=u1, up1a=up1a, up1b=up1b, y=y)
+        ctx.sts = (st3, st2, st1)
+        ctx.params = P
+        ctx.packed = packed
+        if opts.get("keep_acts") is not None:
+            opts["keep_acts"].update(ctx.acts)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        A, P, packed = ctx.acts, ctx.params, ctx.packed
+        st3, st2, st1 = ctx.sts
+        c = A["c"]
+        G = {}
+
+        def wd(name):
+            return packed.get(name, P[name])[1]
+
+        def plain_block_bwd(name, src, a, g_b, mask_src):
+            """Backward of r_double_conv with a single source.  g_b is masked by relu'(b).
+            Returns the gradient at `src`, masked by relu'(mask_src) when given."""
+            cin = P[f"{name}.0.weight"].shape[1]
+            cout = P[f"{name}.0.weight"].shape[0]
+            G[f"{name}.2.weight"], G[f"{name}.2.bias"] = K.conv3x3_wgrad(a, None, g_b)
+            g_a = K.conv3x3(g_b, None, wd(f"{name}.2.weight"), None, False, a, cout)
+            G[f"{name}.0.weight"], G[f"{name}.0.bias"] = K.conv3x3_wgrad(src, None, g_a)
+            return K.conv3x3(g_a, None, wd(f"{name}.0.weight"), None, False, mask_src, cin)
+
+        def up_block_bwd(name, u, skip, a, g_b):
+            """Backward of a decoder r_double_conv fed by the virtual concat [u, skip]."""
+            c0, c1 = u.shape[3], skip.shape[3]
+            cout = a.shape[3]
+            G[f"{name}.2.weight"], G[f"{name}.2.bias"] = K.conv3x3_wgrad(a, None, g_b)
+            g_a = K.conv3x3(g_b, None, wd(f"{name}.2.weight"), None, False, a, cout)
+            G[f"{name}.0.weight"], G[f"{name}.0.bias"] = K.conv3x3_wgrad(u, skip, g_a)
+            w_d = wd(f"{name}.0.weight")  # [c0 + c1][9 * cout]: row slices are the two sources
+            g_u = K.conv3x3(g_a, None, w_d[:c0], None, False, None, c0)
+            g_skip = K.conv3x3(g_a, None, w_d[c0:], None, False, None, c1)
+            return g_u, g_skip
+
+        def adain_bwd(name, g_u, x_in, st):
+            gx, dlw, dlb = K.adain_up_drop_bwd(g_u, x_in, c, P[f"{name}.l1.weight"],
+                                               P[f"{name}.l1.bias"], st)
+            G[f"{name}.l1.weight"], G[f"{name}.l1.bias"] = dlw, dlb
+            return gx
+
+        gy = gy.contiguous().float()
+        g_up1b, G["conv_last.weight"], G["conv_last.bias"] = K.conv_last_tanh_bprop(
+            gy, A["y"], A["up1b"], P["conv_last.weight"])
+        g_u1, g_skip1 = up_block_bwd("dconv_up1", A["u1"], A["conv1"], A["up1a"], g_up1b)
+        g_up2b = adain_bwd("adain1", g_u1, A["up2b"], st1)
+        g_u2, g_skip2 = up_block_bwd("dconv_up2", A["u2"], A["conv2"], A["up2a"], g_up2b)
+        g_up3b = adain_bwd("adain2", g_u2, A["up3b"], st2)
+        g_u3, g_skip3 = up_block_bwd("dconv_up3", A["u3"], A["conv3"], A["up3a"], g_up3b)
+        g_x4 = adain_bwd("adain3", g_u3, A["x4"], st3)
+
+        g_p3 = plain_block_bwd("dconv_down4", A["p3"], A["d4a"], g_x4, None)
+        g_conv3 = K.maxpool2_bwd(A["conv3"], g_p3, g_skip3)
+        g_p2 = plain_block_bwd("dconv_down3", A["p2"], A["d3a"], g_conv3, None)
+        g_conv2 = K.maxpool2_bwd(A["conv2"], g_p2, g_skip2)
+        g_p1 = plain_block_bwd("dconv_down2", A["p1"], A["d2a"], g_conv2, None)
+        g_conv1 = K.maxpool2_bwd(A["conv1"], g_p1, g_skip1)
+
+        G["dconv_down1.2.weight"], G["dconv_down1.2.bias"] = K.conv3x3_wgrad(A["a1"], None, g_conv1)
+        g_a1 = K.conv3x3(g_conv1, None, wd("dconv_down1.2.weight"), None, False, A["a1"], 64)
+        G["dconv_down1.0.weight"], G["dconv_down1.0.bias"] = K.conv_first_wgrad(A["x"], g_a1)
+
+        ctx.acts = None
+        grads = []
+        for i, n in enumerate(PARAM_NAMES):
+            grads.append(G[n].view_as(P[n]) if ctx.needs_input_grad[3 + i] else None)
+        # no gradient for the image or the condition (the reference never asks for them:
+        # t_cls_train.py:242,272 differentiates w.r.t. the generator's parameters only)
+        return (None, None, None) + tuple(grads)
+
+
+def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=None):
+    """Host-side checks (utils.py:42 batch assert, cunet.py H%8 requirement) + the autograd node."""
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"Conditional_UNet expects x of shape (B, 3, H, W), got {tuple(x.shape)}")
+    if c.dim() != 2 or c.shape[1] != module.num_classes:
+        raise ValueError(
+            f"Conditional_UNet expects c of shape (B, {module.num_classes}), got {tuple(c.shape)}")
+    assert x.size(0) == c.size(0)  # same failure mode as utils.py:42
+    if x.shape[2] % 8 or x.shape[3] % 8:
+        raise RuntimeError(
+            f"Sizes of tensors must match: H and W must be divisible by 8, got {tuple(x.shape[2:])}")
+    require_device(x)
+    if c.device != x.device:
+        raise RuntimeError("x and c must be on the same device")
+    if x.requires_grad or c.requires_grad:
+        raise RuntimeError("weather-unet_b200: gradients w.r.t. x or c are not provided "
+                           "(the reference trains the generator's parameters only)")
+    x = x.detach().contiguous().float()
+    c = c.detach().contiguous().float()
+    training = module.training
+    masks = None
+    if dropout_masks is not None:
+        masks = tuple(m.contiguous() for m in dropout_masks)
+        B, H, W = x.shape[0], x.shape[2], x.shape[3]
+        want = [(B, H // 4, W // 4, 512), (B, H // 2, W // 2, 256), (B, H, W, 128)]
+        for m, s in zip(masks, want):
+            if tuple(m.shape) != s or m.dtype != torch.uint8:
+                raise ValueError(f"dropout mask must be uint8 NHWC {s}, got {m.dtype} {tuple(m.shape)}")
+    if seed is None:
+        # host RNG draw (no device sync); three sites use seed, seed+1, seed+2
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+    params = [module.get_parameter(n) for n in PARAM_NAMES]
+    opts = dict(training=training, p=module.dropout.p, masks=masks, seed=seed,
+                eps=(module.adain3.eps, module.adain2.eps, module.adain1.eps),
+                packed=module._packed, keep_acts=keep_acts)
+    return _CUNetFn.apply(x, c, opts, *params)

@@ -1,0 +1,112 @@
+"""ctypes binding of libwu_b200.so (the C ABI declared in include/wu_b200.h).
+
+PyTorch is plumbing here: it owns every buffer and the stream; the arithmetic is in the library.
+There is no CPU / eager fallback: if the shared library is missing or the device is not sm_100,
+the first call raises.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_ulonglong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwu_b200.so")
+
+P, I, F, U64, SZ = c_void_p, c_int, c_float, c_uint64, c_size_t
+
+# name -> (restype, argtypes); mirrors include/wu_b200.h line by line
+SIGNATURES = {
+    "wu_last_error": (c_char_p, []),
+    "wu_version": (I, []),
+    "wu_device_check": (I, []),
+    "wu_launch_count": (c_ulonglong, []),
+    "wu_pack_conv3x3_weights": (I, [P, I, I, P, P, P]),
+    "wu_conv3x3_fprop": (I, [P, I, P, I, P, P, I, P, P, I, I, I, I, P]),
+    "wu_conv3x3_wgrad_workspace_bytes": (SZ, [I, I, I, I, I]),
+    "wu_conv3x3_wgrad": (I, [P, I, P, I, P, I, I, I, I, P, P, P, SZ, P]),
+    "wu_conv_first_fprop": (I, [P, P, P, P, I, I, I, P]),
+    "wu_conv_first_wgrad_workspace_bytes": (SZ, [I, I, I]),
+    "wu_conv_first_wgrad": (I, [P, P, P, P, I, I, I, P, SZ, P]),
+    "wu_conv_last_tanh_fprop": (I, [P, P, P, P, I, I, I, P]),
+    "wu_conv_last_tanh_bprop_workspace_bytes": (SZ, [I, I, I]),
+    "wu_conv_last_tanh_bprop": (I, [P, P, P, P, P, P, P, I, I, I, P, SZ, P]),
+    "wu_maxpool2_fwd": (I, [P, P, I, I, I, I, P]),
+    "wu_maxpool2_bwd": (I, [P, P, P, P, I, I, I, I, P]),
+    "wu_adain_stats_chunks": (I, [I]),
+    "wu_adain_stats": (I, [P, P, I, I, I, P]),
+    "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, P]),
+    "wu_adain_up_drop_fwd": (I, [P, P, P, P, I, I, I, I, F, U64, P, P]),
+    "wu_adain_up_drop_bwd": (I, [P, P, P, P, P, P, I, I, I, I, F, U64, P, P]),
+    "wu_adain_style_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
+    "wu_adain_bwd_apply": (I, [P, P, P, P, P, P, P, P, I, I, I, P]),
+    "wu_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
+    "wu_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),
+}
+
+_lib = None
+
+
+class WuError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WuError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+            " (no CPU fallback exists for the cUNet hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(SIGNATURES)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Call a status-returning entry point; raise WuError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.wu_last_error()
+        raise WuError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def query(name, *args):
+    """Call a value-returning entry point (workspace sizes, counters)."""
+    return getattr(load(), name)(*args)
+
+
+_checked_devices = set()
+
+
+def require_device(t):
+    """The hot path has no CPU path: tensors must live on an sm_100 CUDA device."""
+    if not t.is_cuda:
+        raise WuError("weather-unet_b200: input is not a CUDA tensor and there is no CPU fallback")
+    idx = t.device.index
+    if idx not in _checked_devices:
+        with torch.cuda.device(idx):
+            call("wu_device_check")
+        _checked_devices.add(idx)

@@ -1,0 +1,172 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/wu_b200.h).
+
+Every wrapper allocates its outputs / scratch with torch (the library never allocates), passes raw
+device pointers plus the current CUDA stream, and returns torch tensors.  Activations are NHWC
+bf16 tensors of shape (B, H, W, C).
+"""
+import torch
+
+from . import _lib
+from ._lib import call, ptr, query, stream
+
+BF16 = torch.bfloat16
+
+
+def _act(B, H, W, C, like):
+    return torch.empty((B, H, W, C), dtype=BF16, device=like.device)
+
+
+def pack_conv3x3_weights(w, need_dgrad=True):
+    """fp32 [cout][cin][3][3] -> (bf16 [cout][9*cin], bf16 [cin][9*cout] or None)."""
+    cout, cin = w.shape[0], w.shape[1]
+    wf = torch.empty((cout, 9 * cin), dtype=BF16, device=w.device)
+    wd = torch.empty((cin, 9 * cout), dtype=BF16, device=w.device) if need_dgrad else None
+    call("wu_pack_conv3x3_weights", ptr(w), cout, cin, ptr(wf), ptr(wd), stream())
+    return wf, wd
+
+
+def conv3x3(src0, src1, w_packed, bias, relu, mask, cout):
+    """3x3/s1/p1 convolution over the (virtual) channel concat [src0, src1]; see wu_conv3x3_fprop."""
+    B, H, W, c0 = src0.shape
+    c1 = 0 if src1 is None else src1.shape[3]
+    dst = _act(B, H, W, cout, src0)
+    call("wu_conv3x3_fprop", ptr(src0), c0, ptr(src1), c1, ptr(w_packed), ptr(bias), int(relu),
+         ptr(mask), ptr(dst), cout, B, H, W, stream())
+    return dst
+
+
+def conv3x3_wgrad(src0, src1, dy, want_bias=True):
+    """-> (dw fp32 [cout][cin][3][3], db fp32 [cout] or None)."""
+    B, H, W, c0 = src0.shape
+    c1 = 0 if src1 is None else src1.shape[3]
+    cout = dy.shape[3]
+    cin = c0 + c1
+    nbytes = query("wu_conv3x3_wgrad_workspace_bytes", cin, cout, B, H, W)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dy.device)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dy.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=dy.device) if want_bias else None
+    call("wu_conv3x3_wgrad", ptr(src0), c0, ptr(src1), c1, ptr(dy), cout, B, H, W, ptr(dw), ptr(db),
+         ptr(ws), nbytes, stream())
+    return dw, db
+
+
+def conv_first(x, w, bias):
+    """x fp32 NCHW (B,3,H,W) -> relu(conv3x3) NHWC bf16 (B,H,W,64)."""
+    B, _, H, W = x.shape
+    dst = _act(B, H, W, 64, x)
+    call("wu_conv_first_fprop", ptr(x), ptr(w), ptr(bias), ptr(dst), B, H, W, stream())
+    return dst
+
+
+def conv_first_wgrad(x, dy):
+    B, _, H, W = x.shape
+    nbytes = query("wu_conv_first_wgrad_workspace_bytes", B, H, W)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    dw = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=x.device)
+    db = torch.empty((64,), dtype=torch.float32, device=x.device)
+    call("wu_conv_first_wgrad", ptr(x), ptr(dy), ptr(dw), ptr(db), B, H, W, ptr(ws), nbytes, stream())
+    return dw, db
+
+
+def conv_last_tanh(x, w, bias):
+    """x NHWC bf16 (B,H,W,64) -> tanh(conv1x1) fp32 NCHW (B,3,H,W)."""
+    B, H, W, _ = x.shape
+    y = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    call("wu_conv_last_tanh_fprop", ptr(x), ptr(w), ptr(bias), ptr(y), B, H, W, stream())
+    return y
+
+
+def conv_last_tanh_bprop(gy, y, x, w):
+    B, H, W, _ = x.shape
+    nbytes = query("wu_conv_last_tanh_bprop_workspace_bytes", B, H, W)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    gx = torch.empty_like(x)
+    dw = torch.empty((3, 64, 1, 1), dtype=torch.float32, device=x.device)
+    db = torch.empty((3,), dtype=torch.float32, device=x.device)
+    call("wu_conv_last_tanh_bprop", ptr(gy), ptr(y), ptr(x), ptr(w), ptr(gx), ptr(dw), ptr(db), B, H,
+         W, ptr(ws), nbytes, stream())
+    return gx, dw, db
+
+
+def maxpool2(src):
+    B, H, W, C = src.shape
+    dst = _act(B, H // 2, W // 2, C, src)
+    call("wu_maxpool2_fwd", ptr(src), ptr(dst), B, H, W, C, stream())
+    return dst
+
+
+def maxpool2_bwd(y, g_pool, g_skip):
+    B, H, W, C = y.shape
+    g = torch.empty_like(y)
+    call("wu_maxpool2_bwd", ptr(y), ptr(g_pool), ptr(g_skip), ptr(g), B, H, W, C, stream())
+    return g
+
+
+class AdaINState:
+    """Per-call statistics of one AdaIN site kept for the backward pass (all fp32 [B][C])."""
+    __slots__ = ("mean", "rstd", "ystd", "scale", "shift", "seed", "mask", "p")
+
+
+def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask):
+    """AdaIN(x, cond) -> bilinear x2 (align_corners) -> dropout.  x (B,h,w,C) -> (B,2h,2w,C)."""
+    B, h, w, C = x.shape
+    nc = cond.shape[1]
+    nchunk = query("wu_adain_stats_chunks", h * w)
+    dev = x.device
+    partial = torch.empty((B, nchunk, C, 2), dtype=torch.float32, device=dev)
+    call("wu_adain_stats", ptr(x), ptr(partial), B, h * w, C, stream())
+    st = AdaINState()
+    buf = torch.empty((5, B, C), dtype=torch.float32, device=dev)
+    st.mean, st.rstd, st.ystd, st.scale, st.shift = buf[0], buf[1], buf[2], buf[3], buf[4]
+    st.seed, st.mask, st.p = int(seed), mask, float(p_drop)
+    call("wu_adain_style_fwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.mean), ptr(st.rstd),
+         ptr(st.ystd), ptr(st.scale), ptr(st.shift), B, C, nc, h * w, float(eps), stream())
+    u = _act(B, 2 * h, 2 * w, C, x)
+    call("wu_adain_up_drop_fwd", ptr(x), ptr(st.scale), ptr(st.shift), ptr(u), B, h, w, C, st.p,
+         st.seed, ptr(mask), stream())
+    return u, st
+
+
+def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
+    """-> (gx masked by relu'(x), dlw [4C][nc], dlb [4C])."""
+    B, h, w, C = x.shape
+    nc = cond.shape[1]
+    dev = x.device
+    nchunk = query("wu_adain_stats_chunks", h * w)
+    partial = torch.empty((B, nchunk, C, 2), dtype=torch.float32, device=dev)
+    gz = torch.empty_like(x)
+    call("wu_adain_up_drop_bwd", ptr(gu), ptr(x), ptr(st.mean), ptr(st.rstd), ptr(gz), ptr(partial),
+         B, h, w, C, st.p, st.seed, ptr(st.mask), stream())
+    kk = torch.empty((2, B, C), dtype=torch.float32, device=dev)
+    gh = torch.empty((B, 4 * C), dtype=torch.float32, device=dev)
+    dlw = torch.empty((4 * C, nc), dtype=torch.float32, device=dev)
+    dlb = torch.empty((4 * C,), dtype=torch.float32, device=dev)
+    call("wu_adain_style_bwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.ystd), ptr(kk[0]),
+         ptr(kk[1]), ptr(gh), ptr(dlw), ptr(dlb), B, C, nc, h * w, stream())
+    gx = torch.empty_like(x)
+    call("wu_adain_bwd_apply", ptr(gz), ptr(x), ptr(st.mean), ptr(st.rstd), ptr(st.ystd), ptr(kk[0]),
+         ptr(kk[1]), ptr(gx), B, h * w, C, stream())
+    return gx, dlw, dlb
+
+
+def nchw_to_nhwc(x):
+    """fp32 NCHW -> bf16 NHWC."""
+    B, C, H, W = x.shape
+    dst = _act(B, H, W, C, x)
+    call("wu_nchw_f32_to_nhwc_bf16", ptr(x), ptr(dst), B, C, H, W, stream())
+    return dst
+
+
+def nhwc_to_nchw(x):
+    """bf16 NHWC -> fp32 NCHW."""
+    B, H, W, C = x.shape
+    dst = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    call("wu_nhwc_bf16_to_nchw_f32", ptr(x), ptr(dst), B, C, H, W, stream())
+    return dst
+
+
+def launch_count():
+    return int(query("wu_launch_count"))
+
+
+__all__ = [n for n in dir() if not n.startswith("_")] + ["_lib"]

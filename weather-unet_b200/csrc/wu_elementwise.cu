@@ -1,0 +1,1048 @@
+// wu_elementwise.cu — the HBM-bound kernels of the cUNet generator hot path: first conv (K = 27),
+// last 1x1 conv + tanh, MaxPool2d(2), AdaIN (statistics, style, apply) fused with the bilinear x2
+// upsample and dropout, and their backward passes.  All activations are NHWC bf16; every thread
+// moves 16-byte vectors (8 channels) and all reductions are fp32 (fp64 for the final variance).
+//
+// Reference arithmetic (file:line in the reference tree):
+//   first conv   nets.py:20-21 via cunet.py:21,45        last conv+tanh  cunet.py:39-40,80-82
+//   maxpool      cunet.py:27,46,49,52                    AdaIN           utils.py:26-51
+//   upsample     cunet.py:26,60,67,74                    dropout         cunet.py:28,61,68,75
+#include <cstdio>
+
+#include "wu_host.h"
+#include "wu_ptx.cuh"
+
+namespace wu {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16lo(v.x); f[1] = bf16hi(v.x);
+  f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+  f[4] = bf16lo(v.z); f[5] = bf16hi(v.z);
+  f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+// streaming (read-once / write-once) variants: keep L1 for the reused operands
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// Philox4x32-10 (Salmon et al. 2011): counter = 128-bit, key = 64-bit.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// Keep flags for the 8 channels of vector `vec_index` (16 random bits each, keep iff u16 >= thr).
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t vec_index, uint32_t thr) {
+  const uint4 r = philox4x32_10(
+      make_uint4((uint32_t)vec_index, (uint32_t)(vec_index >> 32), 0x77755555u, 0u),
+      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t keep = 0;
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if ((w[i] & 0xFFFFu) >= thr) keep |= 1u << (2 * i);
+    if ((w[i] >> 16) >= thr) keep |= 1u << (2 * i + 1);
+  }
+  return keep;
+}
+__host__ __device__ inline uint32_t dropout_threshold(float p) {
+  float t = p * 65536.f + 0.5f;
+  if (t < 0.f) t = 0.f;
+  if (t > 65535.f) t = 65535.f;
+  return (uint32_t)t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------------
+// One block transposes a [32 channels][32 pixels] tile through shared memory.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                    int C, long long HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[((long long)b * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    if (c < C && p < HW) dst[((long long)b * HW + p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                    int C, long long HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(src[((long long)b * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[((long long)b * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer: Conv2d(3, 64, 3, padding=1) + ReLU, NCHW fp32 image -> NHWC bf16
+// ------------------------------------------------------------------------------------------------
+// thread = (pixel, 16-channel group); a warp writes 8 pixels x 128 B contiguous.
+__global__ void __launch_bounds__(256)
+conv_first_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int B, int H,
+                        int W) {
+  __shared__ __align__(16) float ws[27][64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+    const int co = i / 27, k = i - co * 27;  // w is [co][ci][r][s] = [co][k]
+    ws[k][co] = w[i];
+  }
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  const int cg = threadIdx.x & 3;
+  for (long long px = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); px < npix;
+       px += (long long)gridDim.x * 64) {
+    const int wq = (int)(px % W);
+    const long long t = px / W;
+    const int hq = (int)(t % H);
+    const int b = (int)(t / H);
+    float in[27];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int hh = hq + r - 1, ww = wq + s - 1;
+          in[ci * 9 + r * 3 + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                                       ? __ldg(x + (((long long)b * 3 + ci) * H + hh) * W + ww)
+                                       : 0.f;
+        }
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = bs[cg * 16 + j];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4* wr = reinterpret_cast<const float4*>(&ws[k][cg * 16]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 wv = wr[j];
+        acc[4 * j + 0] = fmaf(in[k], wv.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(in[k], wv.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(in[k], wv.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(in[k], wv.w, acc[4 * j + 3]);
+      }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+    uint4* o = reinterpret_cast<uint4*>(dst + px * 64 + cg * 16);
+    o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// dw[co][k] = sum_px dy[px][co] * patch[px][k]  (k = ci*9 + r*3 + s, slot 27 == 1 -> db).
+// Block: 256 threads = 4 pixel slices x (16 channel quads x 4 tap octets); 32 accumulators/thread.
+constexpr int kFirstWgradTile = 64;  // pixels staged per iteration
+__global__ void __launch_bounds__(256)
+conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                        float* __restrict__ partial, int B, int H, int W) {
+  __shared__ __align__(16) float sdy[kFirstWgradTile][64];
+  __shared__ __align__(16) float sp[kFirstWgradTile][32];
+  const long long npix = (long long)B * H * W;
+  const long long ntiles = (npix + kFirstWgradTile - 1) / kFirstWgradTile;
+  const int q = threadIdx.x & 15;         // output channels 4q .. 4q+3
+  const int kg = (threadIdx.x >> 4) & 3;  // patch slots 8kg .. 8kg+7
+  const int ps = threadIdx.x >> 6;        // pixel slice
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long p0 = tile * kFirstWgradTile;
+    __syncthreads();
+    // stage dy: 64 px x 64 ch bf16 = 512 x 16 B
+    for (int i = threadIdx.x; i < kFirstWgradTile * 8; i += blockDim.x) {
+      const int p = i >> 3, v = i & 7;
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (p0 + p < npix) unpack8(ld_stream16(dy + (p0 + p) * 64 + v * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sdy[p][v * 8 + e] = f[e];
+    }
+    // stage patches: 64 px x 32 slots
+    for (int i = threadIdx.x; i < kFirstWgradTile * 32; i += blockDim.x) {
+      const int p = i >> 5, k = i & 31;
+      float v = 0.f;
+      const long long px = p0 + p;
+      if (px < npix) {
+        if (k < 27) {
+          const int wq = (int)(px % W);
+          const long long t = px / W;
+          const int hq = (int)(t % H);
+          const int b = (int)(t / H);
+          const int ci = k / 9, rs = k - ci * 9, r = rs / 3, s = rs - r * 3;
+          const int hh = hq + r - 1, ww = wq + s - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+            v = __ldg(x + (((long long)b * 3 + ci) * H + hh) * W + ww);
+        } else if (k == 27) {
+          v = 1.f;
+        }
+      }
+      sp[p][k] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = ps; p < kFirstWgradTile; p += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(&sdy[p][q * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&sp[p][kg * 8]);
+      const float4 c = *reinterpret_cast<const float4*>(&sp[p][kg * 8 + 4]);
+      const float dd[4] = {d.x, d.y, d.z, d.w};
+      const float pp[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dd[i], pp[j], acc[i][j]);
+    }
+  }
+  // fold the 4 pixel slices through shared memory (reuse sdy: 4 x 64 x 32 floats = 32 KB > sdy)
+  __syncthreads();
+  float* red = &sdy[0][0];  // 64 x 64 floats = 16 KB: two passes of two slices
+  float* outp = partial + (size_t)blockIdx.x * 64 * 32;
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((ps >> 1) == pass) {
+      float* r = red + (ps & 1) * 2048;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[(q * 4 + i) * 32 + kg * 8 + j] = acc[i][j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+      const float s = red[i] + red[2048 + i];
+      if (pass == 0) outp[i] = s; else outp[i] += s;
+    }
+    __syncthreads();
+  }
+}
+__global__ void conv_first_wgrad_final_kernel(const float* __restrict__ partial,
+                                              float* __restrict__ dw, float* __restrict__ db,
+                                              int nblocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // co*32 + slot
+  if (i >= 64 * 32) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 2048 + i];
+  const int co = i >> 5, k = i & 31;
+  if (k < 27) dw[co * 27 + k] = s;
+  else if (k == 27 && db != nullptr) db[co] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// last layer: Conv2d(64, 3, 1) + Tanh, NHWC bf16 -> NCHW fp32
+// ------------------------------------------------------------------------------------------------
+// 8 lanes share a pixel (8 channels each); a warp covers 32 consecutive pixels in 8 steps.
+__global__ void __launch_bounds__(256)
+conv_last_tanh_fprop_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                            const float* __restrict__ bias, float* __restrict__ y, long long npix,
+                            long long HW) {
+  __shared__ float so[8][3][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7;
+  float wr[3][8];
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wr[o][e] = __ldg(w + o * 64 + sub * 8 + e);
+  const float b0 = bias ? __ldg(bias) : 0.f, b1 = bias ? __ldg(bias + 1) : 0.f,
+              b2 = bias ? __ldg(bias + 2) : 0.f;
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * 32; base < npix; base += nwarps * 32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long px = base + i * 4 + (lane >> 3);
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (px < npix) unpack8(ld_stream16(x + px * 64 + sub * 8), f);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a0 = fmaf(f[e], wr[0][e], a0);
+        a1 = fmaf(f[e], wr[1][e], a1);
+        a2 = fmaf(f[e], wr[2][e], a2);
+      }
+#pragma unroll
+      for (int m = 1; m < 8; m <<= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, m);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, m);
+      }
+      if (sub == 0) {
+        const int p = i * 4 + (lane >> 3);
+        so[warp][0][p] = tanhf(a0 + b0);
+        so[warp][1][p] = tanhf(a1 + b1);
+        so[warp][2][p] = tanhf(a2 + b2);
+      }
+    }
+    __syncwarp();
+    const long long px = base + lane;
+    if (px < npix) {
+      const long long b = px / HW, r = px - b * HW;
+#pragma unroll
+      for (int o = 0; o < 3; ++o) y[(b * 3 + o) * HW + r] = so[warp][o][lane];
+    }
+    __syncwarp();
+  }
+}
+
+// gx[px][ci] = (x > 0) * sum_o w[o][ci] t[o],  t[o] = gy[o] * (1 - y[o]^2)
+// partial[block][3*64 + 3]: dw[o][ci] = sum_px t[o] x[px][ci], db[o] = sum_px t[o]
+__global__ void __launch_bounds__(256)
+conv_last_tanh_bprop_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                            const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                            __nv_bfloat16* __restrict__ gx, float* __restrict__ partial,
+                            long long npix, long long HW) {
+  __shared__ float st[8][3][32];
+  __shared__ float red[8][4][200];  // [warp][pixel-in-quad lane group][195]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, grp = lane >> 3;
+  float wr[3][8];
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wr[o][e] = __ldg(w + o * 64 + sub * 8 + e);
+  float dw[3][8];
+  float dbl[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dw[o][e] = 0.f;
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * 32; base < npix; base += nwarps * 32) {
+    {
+      const long long px = base + lane;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      if (px < npix) {
+        const long long b = px / HW, r = px - b * HW;
+        const float y0 = y[(b * 3 + 0) * HW + r], y1 = y[(b * 3 + 1) * HW + r],
+                    y2 = y[(b * 3 + 2) * HW + r];
+        t0 = gy[(b * 3 + 0) * HW + r] * (1.f - y0 * y0);
+        t1 = gy[(b * 3 + 1) * HW + r] * (1.f - y1 * y1);
+        t2 = gy[(b * 3 + 2) * HW + r] * (1.f - y2 * y2);
+      }
+      st[warp][0][lane] = t0;
+      st[warp][1][lane] = t1;
+      st[warp][2][lane] = t2;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = i * 4 + grp;
+      const long long px = base + p;
+      const float t0 = st[warp][0][p], t1 = st[warp][1][p], t2 = st[warp][2][p];
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (px < npix) unpack8(ld_stream16(x + px * 64 + sub * 8), f);
+      float g[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dw[0][e] = fmaf(t0, f[e], dw[0][e]);
+        dw[1][e] = fmaf(t1, f[e], dw[1][e]);
+        dw[2][e] = fmaf(t2, f[e], dw[2][e]);
+        const float v = fmaf(t0, wr[0][e], fmaf(t1, wr[1][e], t2 * wr[2][e]));
+        g[e] = f[e] > 0.f ? v : 0.f;
+      }
+      if (sub == 0) {
+        dbl[0] += t0;
+        dbl[1] += t1;
+        dbl[2] += t2;
+      }
+      if (px < npix) st_stream16(gx + px * 64 + sub * 8, pack8(g));
+    }
+    __syncwarp();
+  }
+  // block reduction: each (warp, grp) writes its 8-lane row of 3x64 (+3) values, then fold 32 rows
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][grp][o * 64 + sub * 8 + e] = dw[o][e];
+  if (sub == 0) {
+    red[warp][grp][192] = dbl[0];
+    red[warp][grp][193] = dbl[1];
+    red[warp][grp][194] = dbl[2];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 195; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) s += red[wv][g][i];
+    partial[(size_t)blockIdx.x * 195 + i] = s;
+  }
+}
+__global__ void conv_last_bprop_final_kernel(const float* __restrict__ partial,
+                                             float* __restrict__ dw, float* __restrict__ db,
+                                             int nblocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 195) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 195 + i];
+  if (i < 192) dw[i] = s;
+  else if (db != nullptr) db[i - 192] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool2d(2)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B,
+                    int H, int W, int C) {
+  const int cv = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long t = i / cv;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const __nv_bfloat16* p = src + (((long long)b * H + 2 * ho) * W + 2 * wo) * C + v * 8;
+    float a[8], c[8], d[8], e[8], m[8];
+    unpack8(ld_stream16(p), a);
+    unpack8(ld_stream16(p + C), c);
+    unpack8(ld_stream16(p + (long long)W * C), d);
+    unpack8(ld_stream16(p + (long long)W * C + C), e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(a[j], c[j]), fmaxf(d[j], e[j]));
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8(m);
+  }
+}
+// thread = (pooled pixel, 8 channels): writes the four full-resolution gradients of its window.
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g_pool,
+                    const __nv_bfloat16* __restrict__ g_skip, __nv_bfloat16* __restrict__ g, int B,
+                    int H, int W, int C) {
+  const int cv = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long t = i / cv;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const long long o00 = (((long long)b * H + 2 * ho) * W + 2 * wo) * C + v * 8;
+    const long long offs[4] = {o00, o00 + C, o00 + (long long)W * C, o00 + (long long)W * C + C};
+    float yv[4][8], gs[4][8], gp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unpack8(ld_stream16(y + offs[k]), yv[k]);
+      if (g_skip != nullptr) {
+        unpack8(ld_stream16(g_skip + offs[k]), gs[k]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gs[k][j] = 0.f;
+      }
+    }
+    if (g_pool != nullptr) unpack8(ld_stream16(g_pool + i * 8), gp);
+    float out[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // first maximum in window scan order (h-major), PyTorch's tie rule
+      int am = 0;
+      float mv = yv[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (yv[k][j] > mv) { mv = yv[k][j]; am = k; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        out[k][j] = yv[k][j] > 0.f ? gs[k][j] + (k == am ? gp[j] : 0.f) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st_stream16(g + offs[k], pack8(out[k]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdaIN statistics: per-(b, chunk, c) sums of x and x^2
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatChunk = 256;  // pixels per block
+
+// Shared block reduction over pixel groups for two 8-wide accumulators.
+// red must hold 2 * groups * C floats.
+__device__ __forceinline__ void block_reduce_pairs(float* red, const float (&s1)[8],
+                                                   const float (&s2)[8], int C, int lanes, int g,
+                                                   int l, float* __restrict__ out /* [C][2] */) {
+  const int groups = blockDim.x / lanes;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[(g * C + l * 8 + e) * 2 + 0] = s1[e];
+    red[(g * C + l * 8 + e) * 2 + 1] = s2[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += red[gg * 2 * C + i];
+    out[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adain_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C,
+                   int nchunk) {
+  extern __shared__ float red[];
+  const int lanes = C >> 3, groups = blockDim.x / lanes;
+  const int g = threadIdx.x / lanes, l = threadIdx.x % lanes;
+  const int b = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
+  const int p0 = chunk * kStatChunk;
+  const int p1 = min(HW, p0 + kStatChunk);
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = p0 + g; p < p1; p += groups) {
+    float f[8];
+    unpack8(ldg16(x + ((long long)b * HW + p) * C + l * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s1[e] += f[e];
+      s2[e] = fmaf(f[e], f[e], s2[e]);
+    }
+  }
+  block_reduce_pairs(red, s1, s2, C, lanes, g, l, partial + ((size_t)b * nchunk + chunk) * C * 2);
+}
+
+// style = l1(cond) -> (y_mean, y_std) over the 4 numbers of a channel; combine with x statistics.
+__global__ void adain_style_fwd_kernel(const float* __restrict__ cond, const float* __restrict__ lw,
+                                       const float* __restrict__ lb,
+                                       const float* __restrict__ partial, float* __restrict__ mean,
+                                       float* __restrict__ rstd, float* __restrict__ ystd,
+                                       float* __restrict__ scale, float* __restrict__ shift, int B,
+                                       int C, int nc, int HW, int nchunk, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  float h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = lb[4 * c + j];
+    for (int k = 0; k < nc; ++k) a = fmaf(cond[b * nc + k], lw[(4 * c + j) * nc + k], a);
+    h[j] = a;
+  }
+  const float ym = 0.25f * (h[0] + h[1] + h[2] + h[3]);
+  float yv = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) yv += (h[j] - ym) * (h[j] - ym);
+  const float ys = sqrtf(yv * (1.f / 3.f) + eps);
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float* pp = partial + (((size_t)b * nchunk + k) * C + c) * 2;
+    s1 += (double)pp[0];
+    s2 += (double)pp[1];
+  }
+  const double m = s1 / HW;
+  double var = (s2 - s1 * m) / (HW > 1 ? HW - 1 : 1);
+  if (var < 0.0) var = 0.0;
+  const float r = (float)(1.0 / sqrt(var + (double)eps));
+  mean[i] = (float)m;
+  rstd[i] = r;
+  ystd[i] = ys;
+  const float sc = ys * r;
+  scale[i] = sc;
+  shift[i] = ym - (float)m * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdaIN apply + bilinear x2 (align_corners=True) + dropout
+// ------------------------------------------------------------------------------------------------
+// PyTorch's source index for align_corners=True: src = dst * (in - 1) / (out - 1), in fp32.
+__device__ __forceinline__ void bilinear_src(int dst, float ratio, int in, int& i0, int& i1,
+                                             float& lam) {
+  const float s = ratio * (float)dst;
+  i0 = (int)s;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  lam = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ u, int B,
+                         int h, int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
+                         const uint8_t* __restrict__ mask) {
+  const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
+  const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long t = i / cv;
+    const int X = (int)(t % Wo);
+    t /= Wo;
+    const int Y = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(Y, rh, h, y0, y1, ly);
+    bilinear_src(X, rw, w, x0, x1, lx);
+    const __nv_bfloat16* xb = x + (long long)b * h * w * C + v * 8;
+    float a[8], c[8], d[8], e[8];
+    unpack8(ldg16(xb + ((long long)y0 * w + x0) * C), a);
+    unpack8(ldg16(xb + ((long long)y0 * w + x1) * C), c);
+    unpack8(ldg16(xb + ((long long)y1 * w + x0) * C), d);
+    unpack8(ldg16(xb + ((long long)y1 * w + x1) * C), e);
+    const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
+    const float4* shp = reinterpret_cast<const float4*>(shift + (long long)b * C + v * 8);
+    const float4 sc0 = __ldg(scp), sc1 = __ldg(scp + 1), sh0 = __ldg(shp), sh1 = __ldg(shp + 1);
+    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+    uint32_t keep = 0xFFu;
+    if (thr != 0u) {
+      if (mask != nullptr) {
+        const uint2 mv = *reinterpret_cast<const uint2*>(mask + i * 8);
+        keep = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((mv.x >> (8 * j)) & 0xFFu) keep |= 1u << j;
+          if ((mv.y >> (8 * j)) & 0xFFu) keep |= 1u << (4 + j);
+        }
+      } else {
+        keep = dropout_keep8(seed, (uint64_t)i, thr);
+      }
+    }
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx),
+                w11 = ly * lx;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // bilinear weights sum to 1, so interpolate x first and apply the affine map once
+      const float xi = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
+      const float z = fmaf(xi, sc[j], sh[j]);
+      o[j] = ((keep >> j) & 1u) ? z * inv_keep : 0.f;
+    }
+    st_stream16(u + i * 8, pack8(o));
+  }
+}
+
+// Adjoint: gz[b,y,x,c] = sum_{Y,X} wy(Y->y) wx(X->x) keep/(1-p) gu[b,Y,X,c]; also per-(b,chunk,c)
+// sums S1 = sum gz and S2 = sum gz * xhat.
+__global__ void __launch_bounds__(256)
+adain_up_drop_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ x,
+                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                         __nv_bfloat16* __restrict__ gz, float* __restrict__ partial, int h, int w,
+                         int C, int nchunk, float inv_keep, uint32_t thr, uint64_t seed,
+                         const uint8_t* __restrict__ mask) {
+  extern __shared__ float red[];
+  const int lanes = C >> 3, groups = blockDim.x / lanes;
+  const int g = threadIdx.x / lanes, l = threadIdx.x % lanes;
+  const int b = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
+  const int HW = h * w, Ho = 2 * h, Wo = 2 * w;
+  const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const int p0 = chunk * kStatChunk, p1 = min(HW, p0 + kStatChunk);
+  float mu[8], rs[8];
+  {
+    const float4* mp = reinterpret_cast<const float4*>(mean + (long long)b * C + l * 8);
+    const float4* rp = reinterpret_cast<const float4*>(rstd + (long long)b * C + l * 8);
+    const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    mu[0] = m0.x; mu[1] = m0.y; mu[2] = m0.z; mu[3] = m0.w;
+    mu[4] = m1.x; mu[5] = m1.y; mu[6] = m1.z; mu[7] = m1.w;
+    rs[0] = r0.x; rs[1] = r0.y; rs[2] = r0.z; rs[3] = r0.w;
+    rs[4] = r1.x; rs[5] = r1.y; rs[6] = r1.z; rs[7] = r1.w;
+  }
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = p0 + g; p < p1; p += groups) {
+    const int yy = p / w, xx = p - yy * w;
+    // destination rows whose source interval touches row yy: src in (yy-1, yy+1)
+    int Ylo = 0, Yhi = Ho - 1, Xlo = 0, Xhi = Wo - 1;
+    if (rh > 0.f) {
+      Ylo = max(0, (int)floorf((float)(yy - 1) / rh) - 1);
+      Yhi = min(Ho - 1, (int)ceilf((float)(yy + 1) / rh) + 1);
+    }
+    if (rw > 0.f) {
+      Xlo = max(0, (int)floorf((float)(xx - 1) / rw) - 1);
+      Xhi = min(Wo - 1, (int)ceilf((float)(xx + 1) / rw) + 1);
+    }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int Y = Ylo; Y <= Yhi; ++Y) {
+      int y0, y1;
+      float ly;
+      bilinear_src(Y, rh, h, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == yy) wy += 1.f - ly;
+      if (y1 == yy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int X = Xlo; X <= Xhi; ++X) {
+        int x0, x1;
+        float lx;
+        bilinear_src(X, rw, w, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == xx) wx += 1.f - lx;
+        if (x1 == xx) wx += lx;
+        if (wx == 0.f) continue;
+        const long long vi = (((long long)b * Ho + Y) * Wo + X) * lanes + l;
+        float f[8];
+        unpack8(ldg16(gu + vi * 8), f);
+        uint32_t keep = 0xFFu;
+        if (thr != 0u) {
+          if (mask != nullptr) {
+            const uint2 mv = *reinterpret_cast<const uint2*>(mask + vi * 8);
+            keep = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if ((mv.x >> (8 * j)) & 0xFFu) keep |= 1u << j;
+              if ((mv.y >> (8 * j)) & 0xFFu) keep |= 1u << (4 + j);
+            }
+          } else {
+            keep = dropout_keep8(seed, (uint64_t)vi, thr);
+          }
+        }
+        const float wgt = wy * wx * inv_keep;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((keep >> j) & 1u) acc[j] = fmaf(wgt, f[j], acc[j]);
+      }
+    }
+    const long long off = ((long long)b * HW + p) * C + l * 8;
+    float xv[8];
+    unpack8(ldg16(x + off), xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += acc[j];
+      s2[j] = fmaf(acc[j], (xv[j] - mu[j]) * rs[j], s2[j]);
+    }
+    *reinterpret_cast<uint4*>(gz + off) = pack8(acc);
+  }
+  block_reduce_pairs(red, s1, s2, C, lanes, g, l, partial + ((size_t)b * nchunk + chunk) * C * 2);
+}
+
+// thread per (b, c): fold the partials, emit k1, k2 and the gradient of the 4 style numbers.
+__global__ void adain_style_bwd_kernel(const float* __restrict__ cond, const float* __restrict__ lw,
+                                       const float* __restrict__ lb,
+                                       const float* __restrict__ partial,
+                                       const float* __restrict__ ystd, float* __restrict__ k1,
+                                       float* __restrict__ k2, float* __restrict__ gh, int B, int C,
+                                       int nc, int HW, int nchunk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float* pp = partial + (((size_t)b * nchunk + k) * C + c) * 2;
+    s1 += (double)pp[0];
+    s2 += (double)pp[1];
+  }
+  k1[i] = (float)(s1 / HW);
+  k2[i] = (float)(s2 / (HW > 1 ? HW - 1 : 1));
+  float h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = lb[4 * c + j];
+    for (int k = 0; k < nc; ++k) a = fmaf(cond[b * nc + k], lw[(4 * c + j) * nc + k], a);
+    h[j] = a;
+  }
+  const float ym = 0.25f * (h[0] + h[1] + h[2] + h[3]);
+  const float ys = ystd[i];
+  // d y_mean / d h_j = 1/4 ;  d y_std / d h_j = (h_j - y_mean) / (3 y_std)
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    gh[(size_t)b * 4 * C + 4 * c + j] = (float)s1 * 0.25f + (float)s2 * (h[j] - ym) / (3.f * ys);
+}
+// thread per row r of l1.weight: dlb[r] = sum_b gh[b][r]; dlw[r][k] = sum_b gh[b][r] cond[b][k]
+__global__ void adain_style_bwd_params_kernel(const float* __restrict__ gh,
+                                              const float* __restrict__ cond,
+                                              float* __restrict__ dlw, float* __restrict__ dlb,
+                                              int B, int R, int nc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float sb = 0.f;
+  for (int b = 0; b < B; ++b) sb += gh[(size_t)b * R + r];
+  dlb[r] = sb;
+  for (int k = 0; k < nc; ++k) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(gh[(size_t)b * R + r], cond[b * nc + k], s);
+    dlw[(size_t)r * nc + k] = s;
+  }
+}
+
+// gx = (x > 0) * rstd * ystd * (gz - k1 - xhat * k2)
+__global__ void __launch_bounds__(256)
+adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ gz, const __nv_bfloat16* __restrict__ x,
+                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ ystd, const float* __restrict__ k1,
+                       const float* __restrict__ k2, __nv_bfloat16* __restrict__ gx, int B, int HW,
+                       int C) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * HW * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    const int b = (int)(i / ((long long)HW * cv));
+    const long long pc = (long long)b * C + v * 8;
+    float g[8], xv[8], o[8];
+    unpack8(ld_stream16(gz + i * 8), g);
+    unpack8(ld_stream16(x + i * 8), xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float r = __ldg(rstd + pc + j);
+      const float xh = (xv[j] - __ldg(mean + pc + j)) * r;
+      const float val = r * __ldg(ystd + pc + j) * (g[j] - __ldg(k1 + pc + j) - xh * __ldg(k2 + pc + j));
+      o[j] = xv[j] > 0.f ? val : 0.f;
+    }
+    st_stream16(gx + i * 8, pack8(o));
+  }
+}
+
+static inline int grid_for(long long work_items, int block, int max_waves = 16) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = (long long)num_sms() * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+static inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace wu
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace wu;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int wu_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W,
+                                        wu_stream_t stream) {
+  WU_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "wu_nchw_f32_to_nhwc_bf16: bad args");
+  WU_REQUIRE(B <= 65535, "wu_nchw_f32_to_nhwc_bf16: B=%d too large", B);
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, (bf16*)dst, C, HW);
+  WU_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return WU_OK;
+}
+extern "C" int wu_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W,
+                                        wu_stream_t stream) {
+  WU_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "wu_nhwc_bf16_to_nchw_f32: bad args");
+  WU_REQUIRE(B <= 65535, "wu_nhwc_bf16_to_nchw_f32: B=%d too large", B);
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)src, dst, C, HW);
+  WU_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+  return WU_OK;
+}
+
+extern "C" int wu_conv_first_fprop(const float* x, const float* w, const float* bias, void* dst,
+                                   int B, int H, int W, wu_stream_t stream) {
+  WU_REQUIRE(x && w && dst && B > 0 && H > 0 && W > 0, "wu_conv_first_fprop: bad args");
+  const long long npix = (long long)B * H * W;
+  conv_first_fprop_kernel<<<grid_for(npix, 64, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, w, bias, (bf16*)dst, B, H, W);
+  WU_CHECK_LAUNCH("conv_first_fprop_kernel");
+  return WU_OK;
+}
+static int first_wgrad_blocks(long long npix) {
+  long long tiles = (npix + kFirstWgradTile - 1) / kFirstWgradTile;
+  long long g = 2LL * num_sms();
+  if (g > tiles) g = tiles;
+  return (int)(g < 1 ? 1 : g);
+}
+extern "C" size_t wu_conv_first_wgrad_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)first_wgrad_blocks((long long)B * H * W) * 2048 * sizeof(float);
+}
+extern "C" int wu_conv_first_wgrad(const float* x, const void* dy, float* dw, float* db, int B,
+                                   int H, int W, void* workspace, size_t workspace_bytes,
+                                   wu_stream_t stream) {
+  WU_REQUIRE(x && dy && dw && workspace && B > 0 && H > 0 && W > 0, "wu_conv_first_wgrad: bad args");
+  const int blocks = first_wgrad_blocks((long long)B * H * W);
+  WU_REQUIRE(workspace_bytes >= (size_t)blocks * 2048 * sizeof(float),
+             "wu_conv_first_wgrad: workspace %zu too small", workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv_first_wgrad_kernel<<<blocks, 256, 0, st>>>(x, (const bf16*)dy, (float*)workspace, B, H, W);
+  WU_CHECK_LAUNCH("conv_first_wgrad_kernel");
+  conv_first_wgrad_final_kernel<<<8, 256, 0, st>>>((const float*)workspace, dw, db, blocks);
+  WU_CHECK_LAUNCH("conv_first_wgrad_final_kernel");
+  return WU_OK;
+}
+
+extern "C" int wu_conv_last_tanh_fprop(const void* x, const float* w, const float* bias, float* y,
+                                       int B, int H, int W, wu_stream_t stream) {
+  WU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "wu_conv_last_tanh_fprop: bad args");
+  const long long npix = (long long)B * H * W;
+  conv_last_tanh_fprop_kernel<<<grid_for(npix, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, w, bias, y, npix, (long long)H * W);
+  WU_CHECK_LAUNCH("conv_last_tanh_fprop_kernel");
+  return WU_OK;
+}
+static int last_bprop_blocks(long long npix) { return grid_for(npix, 256, 4); }
+extern "C" size_t wu_conv_last_tanh_bprop_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)last_bprop_blocks((long long)B * H * W) * 195 * sizeof(float);
+}
+extern "C" int wu_conv_last_tanh_bprop(const float* gy, const float* y, const void* x,
+                                       const float* w, void* gx, float* dw, float* db, int B, int H,
+                                       int W, void* workspace, size_t workspace_bytes,
+                                       wu_stream_t stream) {
+  WU_REQUIRE(gy && y && x && w && gx && dw && workspace && B > 0 && H > 0 && W > 0,
+             "wu_conv_last_tanh_bprop: bad args");
+  const long long npix = (long long)B * H * W;
+  const int blocks = last_bprop_blocks(npix);
+  WU_REQUIRE(workspace_bytes >= (size_t)blocks * 195 * sizeof(float),
+             "wu_conv_last_tanh_bprop: workspace %zu too small", workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv_last_tanh_bprop_kernel<<<blocks, 256, 0, st>>>(gy, y, (const bf16*)x, w, (bf16*)gx,
+                                                      (float*)workspace, npix, (long long)H * W);
+  WU_CHECK_LAUNCH("conv_last_tanh_bprop_kernel");
+  conv_last_bprop_final_kernel<<<1, 256, 0, st>>>((const float*)workspace, dw, db, blocks);
+  WU_CHECK_LAUNCH("conv_last_bprop_final_kernel");
+  return WU_OK;
+}
+
+extern "C" int wu_maxpool2_fwd(const void* src, void* dst, int B, int H, int W, int C,
+                               wu_stream_t stream) {
+  WU_REQUIRE(src && dst && B > 0 && H > 0 && W > 0, "wu_maxpool2_fwd: bad args");
+  WU_REQUIRE(C > 0 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0,
+             "wu_maxpool2_fwd: need C %% 8 == 0 and even H, W (C=%d H=%d W=%d)", C, H, W);
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)src, (bf16*)dst, B, H, W, C);
+  WU_CHECK_LAUNCH("maxpool2_fwd_kernel");
+  return WU_OK;
+}
+extern "C" int wu_maxpool2_bwd(const void* y, const void* g_pool, const void* g_skip, void* g,
+                               int B, int H, int W, int C, wu_stream_t stream) {
+  WU_REQUIRE(y && g && B > 0 && H > 0 && W > 0, "wu_maxpool2_bwd: bad args");
+  WU_REQUIRE(C > 0 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0,
+             "wu_maxpool2_bwd: need C %% 8 == 0 and even H, W (C=%d H=%d W=%d)", C, H, W);
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, (const bf16*)g_pool, (const bf16*)g_skip, (bf16*)g, B, H, W, C);
+  WU_CHECK_LAUNCH("maxpool2_bwd_kernel");
+  return WU_OK;
+}
+
+extern "C" int wu_adain_stats_chunks(int HW) { return HW <= 0 ? 0 : (HW + kStatChunk - 1) / kStatChunk; }
+
+#define WU_REQUIRE_ADAIN_C(fn, C)                                                           \
+  WU_REQUIRE((C) >= 8 && (C) <= 2048 && pow2(C), fn ": C=%d must be a power of two in [8, 2048]", C)
+
+extern "C" int wu_adain_stats(const void* x, float* partial, int B, int HW, int C,
+                              wu_stream_t stream) {
+  WU_REQUIRE(x && partial && B > 0 && HW > 0, "wu_adain_stats: bad args");
+  WU_REQUIRE_ADAIN_C("wu_adain_stats", C);
+  const int nchunk = wu_adain_stats_chunks(HW);
+  const int lanes = C / 8, groups = 256 / lanes;
+  adain_stats_kernel<<<B * nchunk, 256, 2 * groups * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)x, partial, HW, C, nchunk);
+  WU_CHECK_LAUNCH("adain_stats_kernel");
+  return WU_OK;
+}
+extern "C" int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb,
+                                  const float* partial, float* mean, float* rstd, float* ystd,
+                                  float* scale, float* shift, int B, int C, int nc, int HW,
+                                  float eps, wu_stream_t stream) {
+  WU_REQUIRE(cond && lw && lb && partial && mean && rstd && ystd && scale && shift,
+             "wu_adain_style_fwd: null pointer");
+  WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0, "wu_adain_style_fwd: bad shape");
+  adain_style_fwd_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      cond, lw, lb, partial, mean, rstd, ystd, scale, shift, B, C, nc, HW,
+      wu_adain_stats_chunks(HW), eps);
+  WU_CHECK_LAUNCH("adain_style_fwd_kernel");
+  return WU_OK;
+}
+extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u,
+                                    int B, int h, int w, int C, float p_drop, uint64_t seed,
+                                    const uint8_t* mask, wu_stream_t stream) {
+  WU_REQUIRE(x && scale && shift && u && B > 0 && h > 0 && w > 0, "wu_adain_up_drop_fwd: bad args");
+  WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_up_drop_fwd: C=%d must be a multiple of 8", C);
+  WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
+  const long long total = (long long)B * 4 * h * w * (C / 8);
+  const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
+  adain_up_drop_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, scale, shift, (bf16*)u, B, h, w, C, 1.f / (1.f - p_drop), thr, seed, mask);
+  WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
+  return WU_OK;
+}
+extern "C" int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean,
+                                    const float* rstd, void* gz, float* partial, int B, int h,
+                                    int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
+                                    wu_stream_t stream) {
+  WU_REQUIRE(gu && x && mean && rstd && gz && partial && B > 0 && h > 0 && w > 0,
+             "wu_adain_up_drop_bwd: bad args");
+  WU_REQUIRE_ADAIN_C("wu_adain_up_drop_bwd", C);
+  WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_bwd: p_drop=%f out of [0,1)", p_drop);
+  const int nchunk = wu_adain_stats_chunks(h * w);
+  const int lanes = C / 8, groups = 256 / lanes;
+  const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
+  adain_up_drop_bwd_kernel<<<B * nchunk, 256, 2 * groups * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)gu, (const bf16*)x, mean, rstd, (bf16*)gz, partial, h, w, C, nchunk,
+      1.f / (1.f - p_drop), thr, seed, mask);
+  WU_CHECK_LAUNCH("adain_up_drop_bwd_kernel");
+  return WU_OK;
+}
+extern "C" int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb,
+                                  const float* partial, const float* ystd, float* k1, float* k2,
+                                  float* gh, float* dlw, float* dlb, int B, int C, int nc, int HW,
+                                  wu_stream_t stream) {
+  WU_REQUIRE(cond && lw && lb && partial && ystd && k1 && k2 && gh && dlw && dlb,
+             "wu_adain_style_bwd: null pointer");
+  WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0, "wu_adain_style_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  adain_style_bwd_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(cond, lw, lb, partial, ystd, k1, k2,
+                                                              gh, B, C, nc, HW,
+                                                              wu_adain_stats_chunks(HW));
+  WU_CHECK_LAUNCH("adain_style_bwd_kernel");
+  adain_style_bwd_params_kernel<<<(4 * C + 127) / 128, 128, 0, st>>>(gh, cond, dlw, dlb, B, 4 * C, nc);
+  WU_CHECK_LAUNCH("adain_style_bwd_params_kernel");
+  return WU_OK;
+}
+extern "C" int wu_adain_bwd_apply(const void* gz, const void* x, const float* mean,
+                                  const float* rstd, const float* ystd, const float* k1,
+                                  const float* k2, void* gx, int B, int HW, int C,
+                                  wu_stream_t stream) {
+  WU_REQUIRE(gz && x && mean && rstd && ystd && k1 && k2 && gx && B > 0 && HW > 0,
+             "wu_adain_bwd_apply: bad args");
+  WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_bwd_apply: C=%d must be a multiple of 8", C);
+  const long long total = (long long)B * HW * (C / 8);
+  adain_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)gz, (const bf16*)x, mean, rstd, ystd, k1, k2, (bf16*)gx, B, HW, C);
+  WU_CHECK_LAUNCH("adain_bwd_apply_kernel");
+  return WU_OK;
+}

@@ -1,0 +1,55 @@
+// wu_host.h — host-side helpers shared by the C-ABI translation units (error slot, TMA maps).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/wu_b200.h"
+
+namespace wu {
+
+// Thread-local last-error slot behind wu_last_error(); returns `code` for `return fail(...)`.
+int fail(int code, const char* fmt, ...);
+
+#define WU_CHECK_CUDA(expr)                                                            \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return ::wu::fail(WU_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,      \
+                        cudaGetErrorString(_e));                                       \
+  } while (0)
+
+#define WU_REQUIRE(cond, ...)                                         \
+  do {                                                                \
+    if (!(cond)) return ::wu::fail(WU_ERR_INVALID, __VA_ARGS__);      \
+  } while (0)
+
+// NHWC bf16 activation view: `ptr` addresses channel 0 of the view, `ctot` is the pixel pitch in
+// channels of the underlying tensor, `c` the number of channels the view exposes.
+// Builds a 4-D (C, W, H, B) tiled map with box (64, bw, bh, 1) and 128-byte swizzle.
+int make_act_tmap(CUtensorMap* out, const void* ptr, int B, int H, int W, int c, int ctot, int bw,
+                  int bh);
+// Row-major bf16 matrix [rows][cols] (cols contiguous), box (64, box_rows), 128-byte swizzle.
+int make_mat_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int box_rows);
+
+// Pick a (bw, bh) pixel box with bw*bh == npix minimising padded work for an H x W image.
+void pick_box(int H, int W, int npix, int* bw, int* bh);
+
+int num_sms();
+
+// Launch accounting behind wu_launch_count().
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// Error check after a kernel launch (launch-configuration errors only; no sync).
+#define WU_CHECK_LAUNCH(what)                                                             \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess)                                                                \
+      return ::wu::fail(WU_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e)); \
+    ::wu::count_launch();                                                                 \
+  } while (0)
+
+}  // namespace wu
