@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — cUNet G+D training throughput (images/s) at 256x256 on N B200s, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels)
+  python bench.py --impl reference [--gpus N] ...                 reference arm: the oracle
+        restatement of the reference's own PyTorch CPU path on the box's host cores
+
+A "step" is one training iteration of the reference trainer (t_cls_train.py:288-312 D update +
+:226-286 G update, supervised branch, estimator term omitted: SURVEY §8d) on one synthetic batch:
+batch 64 per GPU at 256x256 (BASELINE.json configs[1]).  Weak scaling: the per-GPU batch is fixed.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cunet_gd_train_images_per_sec_256x256"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--nc", type=int, default=5)
+    ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline / transfer legs")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), \
+            float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's CPU train step on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_rate(size, nc, batch, steps, warmup):
+    import torch
+    from oracle import train_oracle as T
+    from weather_unet_b200 import Conditional_UNet
+    from weather_unet_b200.disc import SNDisc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    g_sd = Conditional_UNet(nc).state_dict()
+    torch.manual_seed(100)
+    d_sd = SNDisc(nc).state_dict()
+    tr = T.Trainer(g_sd, d_sd, lr=1e-4)
+    g = torch.Generator().manual_seed(1234)
+    images = torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+    c_real = torch.eye(nc)[torch.randint(0, nc, (batch,), generator=g)]
+    c_tgt = torch.eye(nc)[torch.randint(0, nc, (batch,), generator=g)]
+    for _ in range(warmup):
+        tr.step(images, c_real, c_tgt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(images, c_real, c_tgt)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warm = max(1, min(args.warmup, 2))
+    rate, sec, cores = cpu_train_step_rate(args.size, args.nc, args.ref_batch, steps, warm)
+    sample = (f"{steps} timed CPU iterations of the oracle restatement of the reference train step "
+              f"(fp32, torch CPU) at batch {args.ref_batch}, {args.size}x{args.size}, after {warm} warm-up")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"G+D train step, batch {args.ref_batch} (bounded CPU sample), "
+                               f"{args.size}x{args.size}, nc={args.nc}, CPU host cores"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import cunet_oracle as orc_flops  # FLOP bookkeeping only (no compute)
+    from oracle import train_oracle as step_flops
+    from weather_unet_b200 import Conditional_UNet, _ops as K
+    from weather_unet_b200.disc import SNDisc
+    from weather_unet_b200.train_step import GDTrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    B, S, nc = args.batch, args.size, args.nc
+
+    torch.manual_seed(0)
+    G = Conditional_UNet(nc).to(dev).train()
+    torch.manual_seed(100)
+    D = SNDisc(nc).to(dev).train()
+    trainer = GDTrainStep(G, D, lr=1e-4)
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4  # a small ring of distinct pinned host batches
+    host = []
+    for _ in range(n_host):
+        img = (torch.rand(B, 3, S, S, generator=gen) * 2 - 1).pin_memory()
+        cr = torch.eye(nc)[torch.randint(0, nc, (B,), generator=gen)].pin_memory()
+        ct = torch.eye(nc)[torch.randint(0, nc, (B,), generator=gen)].pin_memory()
+        host.append((img, cr, ct))
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up, then the device-resident timed region
+    for i in range(max(3, args.warmup)):
+        trainer.step(*resident[i % n_host])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = K.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses = trainer.step(*resident[i % n_host])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = K.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total / 1e3)
+    last = {k: float(v) for k, v in losses.items()}
+
+    # ---- end to end: pinned host batch -> device every step, losses read back every step
+    stage = [torch.empty_like(t, device=dev) for t in host[0]]
+    d2h_bytes = 0
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        for dst, src in zip(stage, host[i % n_host]):
+            dst.copy_(src, non_blocking=True)
+        losses = trainer.step(*stage)
+        got = torch.stack([losses["d_loss"], losses["g_loss"]]).cpu()  # D2H read of the step result
+        d2h_bytes = got.numel() * got.element_size()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    extras = {}
+    roof = None
+    peak_burst, peak_sust, hbm, peak_src = peaks()
+    if not args.no_extras:
+        # ---- roofline of the dominant kernel family, timed alone with CUDA events on this stream:
+        # the implicit-GEMM convolution at the generator's largest layer (dconv_up1.0: 192 -> 64 at
+        # full resolution, 14.5 GFLOP per image forward), inputs far larger than L2
+        def time_ms(fn, it=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(it):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / it
+
+        layers = [("dconv_down1.2", 64, 0, 64, 1), ("dconv_down2.0", 64, 0, 128, 2),
+                  ("dconv_down2.2", 128, 0, 128, 2), ("dconv_down3.0", 128, 0, 256, 4),
+                  ("dconv_down3.2", 256, 0, 256, 4), ("dconv_down4.0", 256, 0, 512, 8),
+                  ("dconv_down4.2", 512, 0, 512, 8), ("dconv_up3.0", 512, 256, 256, 4),
+                  ("dconv_up3.2", 256, 0, 256, 4), ("dconv_up2.0", 256, 128, 128, 2),
+                  ("dconv_up2.2", 128, 0, 128, 2), ("dconv_up1.0", 128, 64, 64, 1),
+                  ("dconv_up1.2", 64, 0, 64, 1)]
+        per_layer, tot = {}, {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
+        for name, c0, c1, cout, d in layers:
+            h = S // d
+            s0 = torch.randn(B, h, h, c0, device=dev).to(torch.bfloat16)
+            s1 = torch.randn(B, h, h, c1, device=dev).to(torch.bfloat16) if c1 else None
+            dy = torch.randn(B, h, h, cout, device=dev).to(torch.bfloat16)
+            wf, wd = K.pack_conv3x3_weights(torch.randn(cout, c0 + c1, 3, 3, device=dev) * 0.05)
+            bias = torch.zeros(cout, device=dev)
+            fl = 2.0 * 9 * (c0 + c1) * cout * h * h * B
+            tf = time_ms(lambda: K.conv3x3(s0, s1, wf, bias, True, None, cout))
+            if c1:
+                td = time_ms(lambda: (K.conv3x3(dy, None, wd[:c0], None, False, None, c0),
+                                      K.conv3x3(dy, None, wd[c0:], None, False, None, c1)))
+            else:
+                td = time_ms(lambda: K.conv3x3(dy, None, wd, None, False, s0, c0))
+            tw = time_ms(lambda: K.conv3x3_wgrad(s0, s1, dy))
+            per_layer[name] = {"gflop": fl / 1e9, "fprop_tflops": fl / tf / 1e9,
+                               "dgrad_tflops": fl / td / 1e9, "wgrad_tflops": fl / tw / 1e9}
+            for k, t in (("fprop", tf), ("dgrad", td), ("wgrad", tw)):
+                tot[k][0] += fl
+                tot[k][1] += t
+            del s0, s1, dy
+        dom = per_layer["dconv_up1.0"]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64> @ dconv_up1.0 fprop (192->64, "
+                f"{S}x{S}, batch {B})", "achieved": dom["fprop_tflops"], "peak": peak_burst,
+                "unit": "TFLOP/s", "frac": dom["fprop_tflops"] / peak_burst, "traffic": traffic,
+                "peak_source": peak_src + ", burst (kernel timed alone)",
+                "all_layers": {k: {"tflops": v[0] / v[1] / 1e9, "frac": v[0] / v[1] / 1e9 / peak_burst}
+                               for k, v in tot.items()},
+                "per_layer": per_layer}
+        # ---- batched transfer inference (inf_1year_signals.py:98-107): one image x 1024 signals,
+        # sharded by batch across ranks, no collective; train-mode dropout as the reference runs it
+        n_sig = 1024
+        per_rank = n_sig // world
+        img1 = (torch.rand(1, 3, S, S, generator=gen) * 2 - 1).to(dev)
+        sig = torch.randn(per_rank, nc, generator=gen).to(dev)
+        chunk = min(128, per_rank)
+
+        def transfer():
+            with torch.no_grad():
+                for j in range(0, per_rank, chunk):
+                    G(img1.expand(min(chunk, per_rank - j), -1, -1, -1), sig[j:j + chunk])
+        transfer()
+        barrier()
+        e0.record()
+        for _ in range(3):
+            transfer()
+        e1.record()
+        barrier()
+        ms_tr = max_over_ranks(e0.elapsed_time(e1)) / 3
+        extras["transfer"] = {"metric": "batched_transfer_images_per_sec_256x256",
+                              "value": n_sig / (ms_tr / 1e3), "unit": UNIT, "signals": n_sig,
+                              "mode": "train-mode dropout (faithful), sharded by batch, no collective"}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores = cpu_train_step_rate(S, nc, args.ref_batch, 2, 1)
+        cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"2 timed CPU iterations (1 warm-up) of the oracle restatement of the "
+                              f"reference train step, fp32 torch CPU, batch {args.ref_batch}, {S}x{S}"}
+
+    if rank == 0:
+        flops_step = step_flops.step_flops(S, S, B)            # reference-faithful count
+        executed = B * (orc_flops.conv_flops(S, S) * 2          # 2 G forward
+                        + 2 * orc_flops.conv_flops(S, S) - 2 * 9 * 3 * 64 * S * S   # 1 G backward
+                        + 3 * step_flops.disc_conv_flops(S, S)  # 3 D forward
+                        + 5 * step_flops.disc_conv_flops(S, S))  # 2 D full backward + 1 dgrad-only
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"cUNet G + SNDisc D training iteration (t_cls_train.py supervised "
+                                   f"branch, estimator term omitted), batch {B}/GPU, {S}x{S}, nc={nc}",
+                       "per_gpu_batch": B, "global_batch": B * world, "image": f"{S}x{S}",
+                       "parallelism": f"dp{world}",
+                       "l2": "inputs and activations (GBs per step) far exceed the 126 MB L2; no flush",
+                       "generator": "sm_100a kernels (this repo)",
+                       "discriminator": "PyTorch/cuDNN bf16 autocast (SURVEY §8 f1, next row)"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+            "step_tflops": {"executed_conv_flops_per_step": executed,
+                            "achieved": executed * args.steps / (ms_total / 1e3) / 1e12 / world,
+                            "frac_of_sustained_peak": executed * args.steps / (ms_total / 1e3) / 1e12
+                            / world / peak_sust,
+                            "reference_faithful_flops_per_step": flops_step},
+            "losses_last_step": last,
+        }
+        if roof is not None:
+            line["roofline"] = roof
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

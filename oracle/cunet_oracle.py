@@ -19,10 +19,46 @@ BLOCKS = ("dconv_down1", "dconv_down2", "dconv_down3", "dconv_down4", "dconv_up3
           "dconv_up1")
 
 
-def double_conv(sd, name, x):
-    """nets.py:18-24: conv3x3(pad 1) -> ReLU -> conv3x3(pad 1) -> ReLU."""
-    x = F.relu(F.conv2d(x, sd[f"{name}.0.weight"], sd[f"{name}.0.bias"], padding=1))
-    return F.relu(F.conv2d(x, sd[f"{name}.2.weight"], sd[f"{name}.2.bias"], padding=1))
+class _RoundBF16(torch.autograd.Function):
+    """bf16 storage emulation: value and incoming gradient are rounded to bf16 (kept as fp32)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundGradBF16(torch.autograd.Function):
+    """Identity forward, bf16-rounded gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _q(x, on):
+    return _RoundBF16.apply(x) if on else x
+
+
+def _qw(w, on):
+    """bf16-rounded weight in the forward/data-gradient, fp32 master weight receives the gradient."""
+    return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach() if on else w
+
+
+def double_conv(sd, name, x, q=False, q_first=True):
+    """nets.py:18-24: conv3x3(pad 1) -> ReLU -> conv3x3(pad 1) -> ReLU.
+    q: emulate the CUDA path's storage precision (bf16 weights and activations, fp32 accumulate);
+    q_first=False keeps the first convolution's weights in fp32 (the K=27 image layer does)."""
+    x = _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.0.weight"], q and q_first), sd[f"{name}.0.bias"],
+                           padding=1)), q)
+    return _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.2.weight"], q), sd[f"{name}.2.bias"], padding=1)), q)
 
 
 def adain(sd, name, x, c, eps=EPS):
@@ -55,32 +91,38 @@ def dropout(x, mask, train, p=P_DROP):
     return x * (keep / (1 - p)), keep
 
 
-def forward(sd, x, c, train=False, masks=None, p=P_DROP, collect=None):
+def forward(sd, x, c, train=False, masks=None, p=P_DROP, collect=None, emulate_bf16=False):
     """cunet.py:43-82.  `masks`: optional 3 uint8 NHWC keep masks (sites adain3, adain2, adain1).
-    `collect`: optional dict filled with named intermediate activations (NCHW) and drawn masks."""
+    `collect`: optional dict filled with named intermediate activations (NCHW) and drawn masks.
+    `emulate_bf16`: NOT the reference's arithmetic — the same dataflow with values rounded to bf16
+    wherever the CUDA path stores bf16 (conv weights, activations, activation gradients), so that
+    ReLU masks / pooling arg-maxes agree and kernel parity can be checked tightly."""
+    q = emulate_bf16
     masks = masks or (None, None, None)
     keep = lambda k, v: collect.__setitem__(k, v) if collect is not None else None  # noqa: E731
-    conv1 = double_conv(sd, "dconv_down1", x)
-    conv2 = double_conv(sd, "dconv_down2", F.max_pool2d(conv1, 2))
-    conv3 = double_conv(sd, "dconv_down3", F.max_pool2d(conv2, 2))
-    h = double_conv(sd, "dconv_down4", F.max_pool2d(conv3, 2))
+    conv1 = double_conv(sd, "dconv_down1", x, q, q_first=False)
+    conv2 = double_conv(sd, "dconv_down2", F.max_pool2d(conv1, 2), q)
+    conv3 = double_conv(sd, "dconv_down3", F.max_pool2d(conv2, 2), q)
+    h = double_conv(sd, "dconv_down4", F.max_pool2d(conv3, 2), q)
     keep("conv1", conv1), keep("conv2", conv2), keep("conv3", conv3), keep("x4", h)
     for i, (ad, up, skip) in enumerate((("adain3", "dconv_up3", conv3),
                                         ("adain2", "dconv_up2", conv2),
                                         ("adain1", "dconv_up1", conv1))):
-        h = upsample(adain(sd, ad, h, c))
+        z = adain(sd, ad, h, c)
+        h = upsample(_RoundGradBF16.apply(z) if q else z)
         h, m = dropout(h, masks[i], train, p)
+        h = _q(h, q)
         keep(f"u{3 - i}", h), keep(f"mask{3 - i}", m)
-        h = double_conv(sd, up, torch.cat([h, skip], dim=1))  # concat order [x, skip] (cunet.py:62)
+        h = double_conv(sd, up, torch.cat([h, skip], dim=1), q)  # concat order [x, skip] (cunet.py:62)
         keep(f"up{3 - i}b", h)
     out = F.conv2d(h, sd["conv_last.weight"], sd["conv_last.bias"])
     return torch.tanh(out)
 
 
-def forward_backward(sd, x, c, masks, gy, train=True, p=P_DROP):
+def forward_backward(sd, x, c, masks, gy, train=True, p=P_DROP, emulate_bf16=False):
     """Forward + backward of sum(y * gy).  Returns (y, {param name: grad})."""
     leaf = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-    y = forward(leaf, x, c, train=train, masks=masks, p=p)
+    y = forward(leaf, x, c, train=train, masks=masks, p=p, emulate_bf16=emulate_bf16)
     (y * gy).sum().backward()
     grads = {k: v.grad for k, v in leaf.items() if v.requires_grad and v.grad is not None}
     return y.detach(), grads

@@ -1,0 +1,184 @@
+"""One G+D training iteration of the reference's class-/estimator-conditioned trainers
+(t_cls_train.py:288-312 discriminator update, :226-286 generator update, :184-185 optimisers;
+t_est_train.py:214-283 is the same skeleton with real-valued conditions), restated for synthetic
+or user-supplied batches, single GPU or data parallel (one process per GPU, NCCL all-reduce of the
+gradient buckets overlapped with backward).
+
+The generator runs on the sm_100a kernels; the discriminator and the optional frozen
+estimator are ordinary PyTorch modules.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .ops import dis_hinge, gen_hinge, l1_loss
+
+
+class GradBuckets:
+    """Flat fp32 gradient buckets with `param.grad` as views into them (no copies), all-reduced
+    (sum / world) bucket by bucket on a side stream as soon as every gradient of a bucket has been
+    produced.  Parameters whose gradient never arrives (adain*.emb.weight, utils.py:32) are left
+    out by passing `skip`."""
+
+    def __init__(self, named_params, group=None, bucket_bytes=8 << 20, skip=()):
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        params = [(n, p) for n, p in named_params if p.requires_grad and n not in skip]
+        params.reverse()  # gradients are produced in reverse forward order
+        self.buckets, cur, cur_bytes = [], [], 0
+        for n, p in params:
+            cur.append((n, p))
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flat, self.where = [], {}
+        for bi, bucket in enumerate(self.buckets):
+            total = sum(p.numel() for _, p in bucket)
+            dev = bucket[0][1].device
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            off = 0
+            for n, p in bucket:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                self.where[n] = bi
+                off += p.numel()
+            self.flat.append(flat)
+        self.pending = [len(b) for b in self.buckets]
+        self.works = []
+        dev = self.flat[0].device if self.flat else None
+        self.comm_stream = torch.cuda.Stream(device=dev) if (dev is not None and dev.type == "cuda") else None
+        self._hooks = []
+
+    def attach_autograd_hooks(self):
+        """For ordinary PyTorch modules: fire from AccumulateGrad post hooks."""
+        for bucket in self.buckets:
+            for n, p in bucket:
+                self._hooks.append(p.register_post_accumulate_grad_hook(
+                    lambda _p, n=n: self.ready(n)))
+
+    def zero(self):
+        for f in self.flat:
+            f.zero_()
+        self.pending = [len(b) for b in self.buckets]
+
+    def grad_view(self, name):
+        bi = self.where[name]
+        for n, p in self.buckets[bi]:
+            if n == name:
+                return p.grad
+        raise KeyError(name)
+
+    def ready(self, name):
+        """Mark one gradient as final; launch the bucket's all-reduce when it is complete."""
+        bi = self.where.get(name)
+        if bi is None:
+            return
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0 and self.world > 1:
+            flat = self.flat[bi]
+            if self.comm_stream is not None:
+                self.comm_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.comm_stream):
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                    flat.div_(self.world)
+            else:  # CPU / gloo (tests)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.div_(self.world)
+
+    def finish(self):
+        """Make the compute stream wait for the outstanding reductions (call before optimizer.step)."""
+        if self.comm_stream is not None and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.pending = [len(b) for b in self.buckets]
+
+
+class GDTrainStep:
+    """D update then G update, exactly the reference's order and losses.
+
+    estimator: optional frozen module (B,3,H,W)->(B,nc) (t_cls_train.py:172-177).  When given, the
+    weather term g_loss_w = MSE(estimator(fake), target) is added (t_cls_train.py:256,
+    ops.py:37-39); when None (no checkpoint exists offline) g_loss = g_loss_adv + loss_con.
+    """
+
+    def __init__(self, G, D, lr=1e-4, estimator=None, d_autocast=True, eps_con=1e-2, group=None,
+                 overlap=True):
+        self.G, self.D, self.estimator = G, D, estimator
+        self.d_autocast = d_autocast
+        self.eps_con = eps_con  # 1e-2 supervised, 1e-7 otherwise (t_cls_train.py:259-266)
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.g_buckets = self.d_buckets = None
+        if self.distributed:
+            skip = tuple(n for n, _ in G.named_parameters() if n.endswith("emb.weight"))
+            self.g_buckets = GradBuckets(G.named_parameters(), group, skip=skip)
+            self.d_buckets = GradBuckets(D.named_parameters(), group)
+            self.d_buckets.attach_autograd_hooks()
+            if overlap and hasattr(G, "_grad_sink"):
+                G._grad_sink = self.g_buckets  # the generator's backward writes into the buckets
+            else:
+                self.g_buckets.attach_autograd_hooks()
+            for m in (G, D):  # identical replicas to start from
+                for t in list(m.parameters()) + list(m.buffers()):
+                    dist.broadcast(t.data, src=0, group=group)
+        # t_cls_train.py:184-185: Adam, betas (0, 0.999), L2 weight decay lr/20 (not AdamW)
+        self.g_opt = torch.optim.Adam(G.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
+        self.d_opt = torch.optim.Adam(D.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
+
+    def _disc(self, x, c):
+        if self.d_autocast and x.is_cuda:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.D(x, c)[0].float()
+        return self.D(x, c)[0]
+
+    def _zero(self, opt, buckets):
+        if buckets is not None:
+            buckets.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
+
+    def step(self, images, c_real, c_target, masks_d=None, masks_g=None):
+        """images (B,3,H,W) in [-1,1]; c_real = condition of the real images (one-hot label or
+        estimator output); c_target = condition to transfer to.  Returns loss tensors (no sync)."""
+        G, D = self.G, self.D
+        # ---- discriminator update (t_cls_train.py:288-312)
+        self._zero(self.d_opt, self.d_buckets)
+        real = self._disc(images, c_real)
+        with torch.no_grad():  # the reference builds this graph and drops it with .detach() (:302-303)
+            fake_img = G(images, c_target, dropout_masks=masks_d)
+        fake = self._disc(fake_img, c_target)
+        d_loss = dis_hinge(fake, real)
+        d_loss.backward()
+        if self.d_buckets is not None:
+            self.d_buckets.finish()
+        self.d_opt.step()
+        # ---- generator update (t_cls_train.py:226-286)
+        self._zero(self.g_opt, self.g_buckets)
+        d_params = [p for p in D.parameters()]
+        for p in d_params:  # D's weight gradients of this pass are discarded by the reference
+            p.requires_grad_(False)
+        try:
+            fake_img = G(images, c_target, dropout_masks=masks_g)
+            fake = self._disc(fake_img, c_target)
+            g_adv = gen_hinge(fake)
+            g_l1 = l1_loss(fake_img, images)  # logged only (:255)
+            diff = (fake_img - images).abs().mean(dim=(1, 2, 3))
+            lmda = (c_real - c_target).abs().mean(dim=1)
+            loss_con = (diff / (lmda + self.eps_con)).mean()
+            g_loss = g_adv + loss_con
+            g_w = None
+            if self.estimator is not None:
+                g_w = F.mse_loss(self.estimator(fake_img), c_target)
+                g_loss = g_loss + g_w
+            g_loss.backward()
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
+        if self.g_buckets is not None:
+            self.g_buckets.finish()
+        self.g_opt.step()
+        out = {"d_loss": d_loss.detach(), "g_loss": g_loss.detach(), "g_loss_adv": g_adv.detach(),
+               "g_loss_l1": g_l1.detach(), "loss_con": loss_con.detach()}
+        if g_w is not None:
+            out["g_loss_w"] = g_w.detach()
+        return out
