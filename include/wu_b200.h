@@ -115,11 +115,14 @@ int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, 
                          int h, int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
                          wu_stream_t stream);
 /* Backward, step 1: gz = adjoint(dropout o upsample)(gu) at low resolution, plus per-(b,c)
- * partial sums S1 = sum gz, S2 = sum gz * xhat (xhat = (x-mean)*rstd).
+ * partial sums S1 = sum gz, S2 = sum gz * xhat (xhat = (x-mean)*rstd).  Separable: a horizontal
+ * pass (applies the dropout mask) into `scratch` (bf16 [B][2h][w][C],
+ * wu_adain_up_drop_bwd_scratch_bytes), then a vertical pass.
  *   gz bf16 [B][h][w][C]; partial fp32 [B][nchunk][C][2], nchunk = wu_adain_stats_chunks(h*w). */
+size_t wu_adain_up_drop_bwd_scratch_bytes(int B, int h, int w, int C);
 int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean, const float* rstd,
-                         void* gz, float* partial, int B, int h, int w, int C, float p_drop,
-                         uint64_t seed, const uint8_t* mask, wu_stream_t stream);
+                         void* gz, float* partial, void* scratch, int B, int h, int w, int C,
+                         float p_drop, uint64_t seed, const uint8_t* mask, wu_stream_t stream);
 /* Backward, step 2: reduce the partials, emit k1 = S1/N and k2 = S2/(N-1) ([B][C] fp32) and the
  * gradients of l1.weight / l1.bias (utils.py:31,46), overwritten: dlw [4C][nc], dlb [4C].
  * gh is caller scratch, fp32 [B][4C] (gradient of the style vector l1(cond)). */

@@ -37,7 +37,8 @@ SIGNATURES = {
     "wu_adain_stats": (I, [P, P, I, I, I, P]),
     "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, P]),
     "wu_adain_up_drop_fwd": (I, [P, P, P, P, I, I, I, I, F, U64, P, P]),
-    "wu_adain_up_drop_bwd": (I, [P, P, P, P, P, P, I, I, I, I, F, U64, P, P]),
+    "wu_adain_up_drop_bwd_scratch_bytes": (SZ, [I, I, I, I]),
+    "wu_adain_up_drop_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, U64, P, P]),
     "wu_adain_style_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
     "wu_adain_bwd_apply": (I, [P, P, P, P, P, P, P, P, I, I, I, P]),
     "wu_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),

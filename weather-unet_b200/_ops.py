@@ -135,8 +135,9 @@ def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
     nchunk = query("wu_adain_stats_chunks", h * w)
     partial = torch.empty((B, nchunk, C, 2), dtype=torch.float32, device=dev)
     gz = torch.empty_like(x)
+    scratch = torch.empty((B, 2 * h, w, C), dtype=BF16, device=dev)
     call("wu_adain_up_drop_bwd", ptr(gu), ptr(x), ptr(st.mean), ptr(st.rstd), ptr(gz), ptr(partial),
-         B, h, w, C, st.p, st.seed, ptr(st.mask), stream())
+         ptr(scratch), B, h, w, C, st.p, st.seed, ptr(st.mask), stream())
     kk = torch.empty((2, B, C), dtype=torch.float32, device=dev)
     gh = torch.empty((B, 4 * C), dtype=torch.float32, device=dev)
     dlw = torch.empty((4 * C, nc), dtype=torch.float32, device=dev)

@@ -179,74 +179,172 @@ conv_first_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w
   }
 }
 
+// Register-tiled variant for W % 4 == 0: thread = 4 consecutive pixels of a row x 8 channels
+// (32 accumulators, 54 inputs in registers), 8 threads cover the 64 channels of a pixel quad.
+__global__ void __launch_bounds__(256)
+conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int B,
+                           int H, int W) {
+  __shared__ __align__(16) float ws[27][64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+    const int co = i / 27, k = i - co * 27;
+    ws[k][co] = w[i];
+  }
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int Wq = W >> 2;
+  const long long nquad = (long long)B * H * Wq;
+  const int cg = threadIdx.x & 7;
+  for (long long qd = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); qd < nquad;
+       qd += (long long)gridDim.x * 32) {
+    const int wq = (int)(qd % Wq) * 4;
+    const long long t = qd / Wq;
+    const int hq = (int)(t % H);
+    const int b = (int)(t / H);
+    float in[3][3][6];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = hq + r - 1;
+        const float* row = x + (((long long)b * 3 + ci) * H + hh) * W;
+        const bool hv = hh >= 0 && hh < H;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const int ww = wq + c - 1;
+          in[ci][r][c] = (hv && ww >= 0 && ww < W) ? __ldg(row + ww) : 0.f;
+        }
+      }
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = bs[cg * 8 + j];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+          const float4* wr = reinterpret_cast<const float4*>(&ws[ci * 9 + r * 3 + s3][cg * 8]);
+          const float4 w0 = wr[0], w1 = wr[1];
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float xv = in[ci][r][p + s3];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xv, wv[j], acc[p][j]);
+          }
+        }
+    const long long px0 = ((long long)b * H + hq) * W + wq;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(acc[p][j], 0.f);
+      *reinterpret_cast<uint4*>(dst + (px0 + p) * 64 + cg * 8) = pack8(o);
+    }
+  }
+}
+
 // dw[co][k] = sum_px dy[px][co] * patch[px][k]  (k = ci*9 + r*3 + s, slot 27 == 1 -> db).
 // Block: 256 threads = 4 pixel slices x (16 channel quads x 4 tap octets); 32 accumulators/thread.
+// Tiles of 64 pixels are double-buffered: the next tile's global loads are in flight (registers)
+// while the current tile is multiplied out of shared memory.
 constexpr int kFirstWgradTile = 64;  // pixels staged per iteration
 __global__ void __launch_bounds__(256)
 conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                         float* __restrict__ partial, int B, int H, int W) {
-  __shared__ __align__(16) float sdy[kFirstWgradTile][64];
-  __shared__ __align__(16) float sp[kFirstWgradTile][32];
+  __shared__ __align__(16) __nv_bfloat16 sdy[2][kFirstWgradTile][64];
+  __shared__ __align__(16) float sp[2][kFirstWgradTile][32];
+  __shared__ __align__(16) float red[4096];
   const long long npix = (long long)B * H * W;
   const long long ntiles = (npix + kFirstWgradTile - 1) / kFirstWgradTile;
   const int q = threadIdx.x & 15;         // output channels 4q .. 4q+3
   const int kg = (threadIdx.x >> 4) & 3;  // patch slots 8kg .. 8kg+7
   const int ps = threadIdx.x >> 6;        // pixel slice
+  const int sp_p = threadIdx.x >> 2, sp_part = threadIdx.x & 3;  // staging role: (pixel, channel)
   float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  uint4 rdy[2];
+  float rp[9];
+  auto fetch = [&](long long tile) {
     const long long p0 = tile * kFirstWgradTile;
-    __syncthreads();
-    // stage dy: 64 px x 64 ch bf16 = 512 x 16 B
-    for (int i = threadIdx.x; i < kFirstWgradTile * 8; i += blockDim.x) {
-      const int p = i >> 3, v = i & 7;
-      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (p0 + p < npix) unpack8(ld_stream16(dy + (p0 + p) * 64 + v * 8), f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sdy[p][v * 8 + e] = f[e];
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + i * 256;  // 512 x 16 B
+      const long long px = p0 + (idx >> 3);
+      rdy[i] = px < npix ? ld_stream16(dy + px * 64 + (idx & 7) * 8) : make_uint4(0, 0, 0, 0);
     }
-    // stage patches: 64 px x 32 slots
-    for (int i = threadIdx.x; i < kFirstWgradTile * 32; i += blockDim.x) {
-      const int p = i >> 5, k = i & 31;
-      float v = 0.f;
-      const long long px = p0 + p;
-      if (px < npix) {
-        if (k < 27) {
-          const int wq = (int)(px % W);
-          const long long t = px / W;
-          const int hq = (int)(t % H);
-          const int b = (int)(t / H);
-          const int ci = k / 9, rs = k - ci * 9, r = rs / 3, s = rs - r * 3;
-          const int hh = hq + r - 1, ww = wq + s - 1;
-          if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-            v = __ldg(x + (((long long)b * 3 + ci) * H + hh) * W + ww);
-        } else if (k == 27) {
-          v = 1.f;
-        }
+    const long long px = p0 + sp_p;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) rp[j] = 0.f;
+    if (px < npix) {
+      if (sp_part < 3) {
+        const int wq = (int)(px % W);
+        const long long t = px / W;
+        const int hq = (int)(t % H);
+        const int b = (int)(t / H);
+        const float* plane = x + ((long long)b * 3 + sp_part) * H * W;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int hh = hq + r - 1, ww = wq + c - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) rp[r * 3 + c] = __ldg(plane + (long long)hh * W + ww);
+          }
+      } else {
+        rp[0] = 1.f;  // slot 27: bias gradient
       }
-      sp[p][k] = v;
     }
-    __syncthreads();
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      *reinterpret_cast<uint4*>(&sdy[buf][idx >> 3][(idx & 7) * 8]) = rdy[i];
+    }
+    if (sp_part < 3) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) sp[buf][sp_p][sp_part * 9 + j] = rp[j];
+    } else {
+      sp[buf][sp_p][27] = rp[0];
+#pragma unroll
+      for (int j = 28; j < 32; ++j) sp[buf][sp_p][j] = 0.f;
+    }
+  };
+
+  int buf = 0;
+  if ((long long)blockIdx.x < ntiles) {
+    fetch(blockIdx.x);
+    commit(0);
+  }
+  __syncthreads();
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) fetch(next);
 #pragma unroll 4
     for (int p = ps; p < kFirstWgradTile; p += 4) {
-      const float4 d = *reinterpret_cast<const float4*>(&sdy[p][q * 4]);
-      const float4 a = *reinterpret_cast<const float4*>(&sp[p][kg * 8]);
-      const float4 c = *reinterpret_cast<const float4*>(&sp[p][kg * 8 + 4]);
-      const float dd[4] = {d.x, d.y, d.z, d.w};
+      const uint2 dv = *reinterpret_cast<const uint2*>(&sdy[buf][p][q * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&sp[buf][p][kg * 8]);
+      const float4 c = *reinterpret_cast<const float4*>(&sp[buf][p][kg * 8 + 4]);
+      const float dd[4] = {bf16lo(dv.x), bf16hi(dv.x), bf16lo(dv.y), bf16hi(dv.y)};
       const float pp[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dd[i], pp[j], acc[i][j]);
     }
+    if (next < ntiles) commit(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
   }
-  // fold the 4 pixel slices through shared memory (reuse sdy: 4 x 64 x 32 floats = 32 KB > sdy)
-  __syncthreads();
-  float* red = &sdy[0][0];  // 64 x 64 floats = 16 KB: two passes of two slices
+  // fold the 4 pixel slices through shared memory, two slices per pass
   float* outp = partial + (size_t)blockIdx.x * 64 * 32;
   for (int pass = 0; pass < 2; ++pass) {
     if ((ps >> 1) == pass) {
@@ -258,8 +356,8 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
-      const float s = red[i] + red[2048 + i];
-      if (pass == 0) outp[i] = s; else outp[i] += s;
+      const float sum = red[i] + red[2048 + i];
+      if (pass == 0) outp[i] = sum; else outp[i] += sum;
     }
     __syncthreads();
   }
@@ -601,81 +699,124 @@ __device__ __forceinline__ void bilinear_src(int dst, float ratio, int in, int& 
   lam = s - (float)i0;
 }
 
-__global__ void __launch_bounds__(256)
-adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
-                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ u, int B,
-                         int h, int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
-                         const uint8_t* __restrict__ mask) {
-  const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
-  const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
-  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const long long total = (long long)B * Ho * Wo * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cv);
-    long long t = i / cv;
-    const int X = (int)(t % Wo);
-    t /= Wo;
-    const int Y = (int)(t % Ho);
-    const int b = (int)(t / Ho);
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilinear_src(Y, rh, h, y0, y1, ly);
-    bilinear_src(X, rw, w, x0, x1, lx);
-    const __nv_bfloat16* xb = x + (long long)b * h * w * C + v * 8;
-    float a[8], c[8], d[8], e[8];
-    unpack8(ldg16(xb + ((long long)y0 * w + x0) * C), a);
-    unpack8(ldg16(xb + ((long long)y0 * w + x1) * C), c);
-    unpack8(ldg16(xb + ((long long)y1 * w + x0) * C), d);
-    unpack8(ldg16(xb + ((long long)y1 * w + x1) * C), e);
-    const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
-    const float4* shp = reinterpret_cast<const float4*>(shift + (long long)b * C + v * 8);
-    const float4 sc0 = __ldg(scp), sc1 = __ldg(scp + 1), sh0 = __ldg(shp), sh1 = __ldg(shp + 1);
-    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-    uint32_t keep = 0xFFu;
-    if (thr != 0u) {
-      if (mask != nullptr) {
-        const uint2 mv = *reinterpret_cast<const uint2*>(mask + i * 8);
-        keep = 0;
+// keep flags for 8 consecutive channels: injected uint8 mask or the Philox stream
+__device__ __forceinline__ uint32_t keep_bits8(uint32_t thr, uint64_t seed,
+                                               const uint8_t* __restrict__ mask, long long vi) {
+  if (thr == 0u) return 0xFFu;
+  if (mask != nullptr) {
+    const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mask + vi * 8));
+    uint32_t keep = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if ((mv.x >> (8 * j)) & 0xFFu) keep |= 1u << j;
-          if ((mv.y >> (8 * j)) & 0xFFu) keep |= 1u << (4 + j);
-        }
-      } else {
-        keep = dropout_keep8(seed, (uint64_t)i, thr);
-      }
+    for (int j = 0; j < 4; ++j) {
+      if ((mv.x >> (8 * j)) & 0xFFu) keep |= 1u << j;
+      if ((mv.y >> (8 * j)) & 0xFFu) keep |= 1u << (4 + j);
     }
-    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx),
-                w11 = ly * lx;
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // bilinear weights sum to 1, so interpolate x first and apply the affine map once
-      const float xi = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
-      const float z = fmaf(xi, sc[j], sh[j]);
-      o[j] = ((keep >> j) & 1u) ? z * inv_keep : 0.f;
-    }
-    st_stream16(u + i * 8, pack8(o));
+    return keep;
   }
+  return dropout_keep8(seed, (uint64_t)vi, thr);
 }
 
-// Adjoint: gz[b,y,x,c] = sum_{Y,X} wy(Y->y) wx(X->x) keep/(1-p) gu[b,Y,X,c]; also per-(b,chunk,c)
-// sums S1 = sum gz and S2 = sum gz * xhat.
+// grid = (ceil(2w * C/8 / 256), B * 2h): one block row per output image row, no index divisions
+// by runtime 64-bit quantities in the hot path.
 __global__ void __launch_bounds__(256)
-adain_up_drop_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ x,
-                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                         __nv_bfloat16* __restrict__ gz, float* __restrict__ partial, int h, int w,
-                         int C, int nchunk, float inv_keep, uint32_t thr, uint64_t seed,
+adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ u, int h,
+                         int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
                          const uint8_t* __restrict__ mask) {
+  const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
+  const int xi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xi >= Wo * cv) return;
+  const int X = xi / cv, v = xi - X * cv;
+  const int b = blockIdx.y / Ho, Y = blockIdx.y - b * Ho;
+  const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src(Y, rh, h, y0, y1, ly);
+  bilinear_src(X, rw, w, x0, x1, lx);
+  const __nv_bfloat16* xb = x + (long long)b * h * w * C + v * 8;
+  float a[8], c[8], d[8], e[8];
+  unpack8(ldg16(xb + ((long long)y0 * w + x0) * C), a);
+  unpack8(ldg16(xb + ((long long)y0 * w + x1) * C), c);
+  unpack8(ldg16(xb + ((long long)y1 * w + x0) * C), d);
+  unpack8(ldg16(xb + ((long long)y1 * w + x1) * C), e);
+  const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
+  const float4* shp = reinterpret_cast<const float4*>(shift + (long long)b * C + v * 8);
+  const float4 sc0 = __ldg(scp), sc1 = __ldg(scp + 1), sh0 = __ldg(shp), sh1 = __ldg(shp + 1);
+  const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+  const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+  const long long vi = ((long long)blockIdx.y * Wo + X) * cv + v;
+  const uint32_t keep = keep_bits8(thr, seed, mask, vi);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx),
+              w11 = ly * lx;
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    // bilinear weights sum to 1, so interpolate x first and apply the affine map once
+    const float xi2 = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
+    const float z = fmaf(xi2, sc[j], sh[j]);
+    o[j] = ((keep >> j) & 1u) ? z * inv_keep : 0.f;
+  }
+  st_stream16(u + vi * 8, pack8(o));
+}
+
+// Weight with which destination index D contributes to source index s (0 if it does not).
+__device__ __forceinline__ float bilinear_adjoint_w(int D, int s, float ratio, int in, int out) {
+  if (D < 0 || D >= out) return 0.f;
+  int i0, i1;
+  float lam;
+  bilinear_src(D, ratio, in, i0, i1, lam);
+  float wgt = 0.f;
+  if (i0 == s) wgt += 1.f - lam;
+  if (i1 == s) wgt += lam;
+  return wgt;
+}
+
+// Adjoint of dropout o upsample, separable.  Pass 1 (horizontal, applies the dropout mask):
+//   t[b,Y,x,c] = sum_X wx(X->x) keep(b,Y,X,c)/(1-p) gu[b,Y,X,c],  X in [2x-2, 2x+3]
+// grid = (ceil(w * C/8 / 256), B * 2h).
+__global__ void __launch_bounds__(256)
+adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ t, int h,
+                        int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
+                        const uint8_t* __restrict__ mask) {
+  const int cv = C >> 3, Wo = 2 * w;
+  const int xi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xi >= w * cv) return;
+  const int xx = xi / cv, v = xi - xx * cv;
+  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const long long row = (long long)blockIdx.y * Wo;  // (b, Y) row of the full-resolution tensor
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int X = 2 * xx - 2 + j;
+    const float wx = bilinear_adjoint_w(X, xx, rw, w, Wo);
+    if (wx != 0.f) {
+      const long long vi = (row + X) * cv + v;
+      float f[8];
+      unpack8(ld_stream16(gu + vi * 8), f);
+      const uint32_t keep = keep_bits8(thr, seed, mask, vi);
+      const float wgt = wx * inv_keep;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if ((keep >> e) & 1u) acc[e] = fmaf(wgt, f[e], acc[e]);
+    }
+  }
+  *reinterpret_cast<uint4*>(t + (((long long)blockIdx.y * w + xx) * cv + v) * 8) = pack8(acc);
+}
+
+// Pass 2 (vertical) + per-(b,chunk,c) sums S1 = sum gz, S2 = sum gz * xhat:
+//   gz[b,y,x,c] = sum_Y wy(Y->y) t[b,Y,x,c],  Y in [2y-2, 2y+3]
+__global__ void __launch_bounds__(256)
+adain_up_vpass_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ x,
+                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                      __nv_bfloat16* __restrict__ gz, float* __restrict__ partial, int h, int w,
+                      int C, int nchunk) {
   extern __shared__ float red[];
   const int lanes = C >> 3, groups = blockDim.x / lanes;
   const int g = threadIdx.x / lanes, l = threadIdx.x % lanes;
   const int b = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
-  const int HW = h * w, Ho = 2 * h, Wo = 2 * w;
+  const int HW = h * w, Ho = 2 * h;
   const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
-  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
   const int p0 = chunk * kStatChunk, p1 = min(HW, p0 + kStatChunk);
   float mu[8], rs[8];
   {
@@ -690,54 +831,16 @@ adain_up_drop_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int p = p0 + g; p < p1; p += groups) {
     const int yy = p / w, xx = p - yy * w;
-    // destination rows whose source interval touches row yy: src in (yy-1, yy+1)
-    int Ylo = 0, Yhi = Ho - 1, Xlo = 0, Xhi = Wo - 1;
-    if (rh > 0.f) {
-      Ylo = max(0, (int)floorf((float)(yy - 1) / rh) - 1);
-      Yhi = min(Ho - 1, (int)ceilf((float)(yy + 1) / rh) + 1);
-    }
-    if (rw > 0.f) {
-      Xlo = max(0, (int)floorf((float)(xx - 1) / rw) - 1);
-      Xhi = min(Wo - 1, (int)ceilf((float)(xx + 1) / rw) + 1);
-    }
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int Y = Ylo; Y <= Yhi; ++Y) {
-      int y0, y1;
-      float ly;
-      bilinear_src(Y, rh, h, y0, y1, ly);
-      float wy = 0.f;
-      if (y0 == yy) wy += 1.f - ly;
-      if (y1 == yy) wy += ly;
-      if (wy == 0.f) continue;
-      for (int X = Xlo; X <= Xhi; ++X) {
-        int x0, x1;
-        float lx;
-        bilinear_src(X, rw, w, x0, x1, lx);
-        float wx = 0.f;
-        if (x0 == xx) wx += 1.f - lx;
-        if (x1 == xx) wx += lx;
-        if (wx == 0.f) continue;
-        const long long vi = (((long long)b * Ho + Y) * Wo + X) * lanes + l;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int Y = 2 * yy - 2 + j;
+      const float wy = bilinear_adjoint_w(Y, yy, rh, h, Ho);
+      if (wy != 0.f) {
         float f[8];
-        unpack8(ldg16(gu + vi * 8), f);
-        uint32_t keep = 0xFFu;
-        if (thr != 0u) {
-          if (mask != nullptr) {
-            const uint2 mv = *reinterpret_cast<const uint2*>(mask + vi * 8);
-            keep = 0;
+        unpack8(ld_stream16(t + ((((long long)b * Ho + Y) * w + xx) * lanes + l) * 8), f);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if ((mv.x >> (8 * j)) & 0xFFu) keep |= 1u << j;
-              if ((mv.y >> (8 * j)) & 0xFFu) keep |= 1u << (4 + j);
-            }
-          } else {
-            keep = dropout_keep8(seed, (uint64_t)vi, thr);
-          }
-        }
-        const float wgt = wy * wx * inv_keep;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if ((keep >> j) & 1u) acc[j] = fmaf(wgt, f[j], acc[j]);
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wy, f[e], acc[e]);
       }
     }
     const long long off = ((long long)b * HW + p) * C + l * 8;
@@ -872,6 +975,12 @@ extern "C" int wu_conv_first_fprop(const float* x, const float* w, const float* 
                                    int B, int H, int W, wu_stream_t stream) {
   WU_REQUIRE(x && w && dst && B > 0 && H > 0 && W > 0, "wu_conv_first_fprop: bad args");
   const long long npix = (long long)B * H * W;
+  if (W % 4 == 0) {
+    conv_first_fprop_x4_kernel<<<grid_for(npix / 4, 32, 16), 256, 0, (cudaStream_t)stream>>>(
+        x, w, bias, (bf16*)dst, B, H, W);
+    WU_CHECK_LAUNCH("conv_first_fprop_x4_kernel");
+    return WU_OK;
+  }
   conv_first_fprop_kernel<<<grid_for(npix, 64, 8), 256, 0, (cudaStream_t)stream>>>(
       x, w, bias, (bf16*)dst, B, H, W);
   WU_CHECK_LAUNCH("conv_first_fprop_kernel");
@@ -993,28 +1102,40 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
   WU_REQUIRE(x && scale && shift && u && B > 0 && h > 0 && w > 0, "wu_adain_up_drop_fwd: bad args");
   WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_up_drop_fwd: C=%d must be a multiple of 8", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
-  const long long total = (long long)B * 4 * h * w * (C / 8);
+  WU_REQUIRE((long long)B * 2 * h <= 65535, "wu_adain_up_drop_fwd: B*2h=%lld exceeds 65535",
+             (long long)B * 2 * h);
   const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
-  adain_up_drop_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, scale, shift, (bf16*)u, B, h, w, C, 1.f / (1.f - p_drop), thr, seed, mask);
+  dim3 grid((unsigned)((2 * w * (C / 8) + 255) / 256), (unsigned)(B * 2 * h));
+  adain_up_drop_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, scale, shift, (bf16*)u, h, w, C, 1.f / (1.f - p_drop), thr, seed, mask);
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
   return WU_OK;
 }
+extern "C" size_t wu_adain_up_drop_bwd_scratch_bytes(int B, int h, int w, int C) {
+  if (B <= 0 || h <= 0 || w <= 0 || C <= 0) return 0;
+  return (size_t)B * 2 * h * w * C * sizeof(bf16);
+}
 extern "C" int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean,
-                                    const float* rstd, void* gz, float* partial, int B, int h,
-                                    int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
-                                    wu_stream_t stream) {
-  WU_REQUIRE(gu && x && mean && rstd && gz && partial && B > 0 && h > 0 && w > 0,
+                                    const float* rstd, void* gz, float* partial, void* scratch,
+                                    int B, int h, int w, int C, float p_drop, uint64_t seed,
+                                    const uint8_t* mask, wu_stream_t stream) {
+  WU_REQUIRE(gu && x && mean && rstd && gz && partial && scratch && B > 0 && h > 0 && w > 0,
              "wu_adain_up_drop_bwd: bad args");
   WU_REQUIRE_ADAIN_C("wu_adain_up_drop_bwd", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_bwd: p_drop=%f out of [0,1)", p_drop);
+  WU_REQUIRE((long long)B * 2 * h <= 65535, "wu_adain_up_drop_bwd: B*2h=%lld exceeds 65535",
+             (long long)B * 2 * h);
   const int nchunk = wu_adain_stats_chunks(h * w);
   const int lanes = C / 8, groups = 256 / lanes;
   const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
-  adain_up_drop_bwd_kernel<<<B * nchunk, 256, 2 * groups * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)gu, (const bf16*)x, mean, rstd, (bf16*)gz, partial, h, w, C, nchunk,
-      1.f / (1.f - p_drop), thr, seed, mask);
-  WU_CHECK_LAUNCH("adain_up_drop_bwd_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((w * (C / 8) + 255) / 256), (unsigned)(B * 2 * h));
+  adain_drop_hpass_kernel<<<grid, 256, 0, st>>>((const bf16*)gu, (bf16*)scratch, h, w, C,
+                                                1.f / (1.f - p_drop), thr, seed, mask);
+  WU_CHECK_LAUNCH("adain_drop_hpass_kernel");
+  adain_up_vpass_kernel<<<B * nchunk, 256, 2 * groups * C * sizeof(float), st>>>(
+      (const bf16*)scratch, (const bf16*)x, mean, rstd, (bf16*)gz, partial, h, w, C, nchunk);
+  WU_CHECK_LAUNCH("adain_up_vpass_kernel");
   return WU_OK;
 }
 extern "C" int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb,

@@ -106,6 +106,9 @@ class GDTrainStep:
                  overlap=True):
         self.G, self.D, self.estimator = G, D, estimator
         self.d_autocast = d_autocast
+        self.d_channels_last = next(D.parameters()).is_cuda
+        if self.d_channels_last:  # cuDNN's bf16 tensor-core kernels are NHWC: avoid per-conv transposes
+            D.to(memory_format=torch.channels_last)
         self.eps_con = eps_con  # 1e-2 supervised, 1e-7 otherwise (t_cls_train.py:259-266)
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.g_buckets = self.d_buckets = None
@@ -126,6 +129,8 @@ class GDTrainStep:
         self.d_opt = torch.optim.Adam(D.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
 
     def _disc(self, x, c):
+        if self.d_channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
         if self.d_autocast and x.is_cuda:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return self.D(x, c)[0].float()
