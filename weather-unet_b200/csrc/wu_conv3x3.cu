@@ -15,6 +15,7 @@
 //   Epilogue: tcgen05.ld -> bias/ReLU/mask -> bf16 -> swizzled smem staging -> TMA store (clips).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane quarter = warp % 4).
 #include <cstdio>
+#include <cstdlib>
 
 #include "wu_host.h"
 #include "wu_ptx.cuh"
@@ -296,6 +297,277 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   conv3x3_igemm_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_kernel");
   return WU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fprop / dgrad, v2: operand reuse in shared memory
+// ------------------------------------------------------------------------------------------------
+// v1 above fetches one (tap, channel block) A tile per MMA group, i.e. every input pixel crosses
+// L2 -> SMEM nine times, and every weight tile once per 128 output pixels; the N = 64 / 128 layers
+// are L2-bandwidth bound that way (ncu: tensor pipe 31 % / 57 %).  v2 changes the tiling:
+//   * output super-tile = T vertically stacked M-tiles of 16 rows x 8 columns (T*128 pixels);
+//   * A: per 64-channel block only THREE TMA boxes (64 ch, 8 px, 16T+2 rows), one per column shift
+//     s-1 in {-1, 0, +1}.  A row shift r is a start-address offset of r KiB (8 pixels x 128 B), which
+//     keeps every UMMA descriptor 1024-byte aligned, so the three taps (r, s) of a column shift and
+//     all T M-tiles read the same copy: A traffic drops from 9 x 16 KiB to 3 x (16T+2) KiB per T tiles;
+//   * B: one (tap, channel block) weight tile feeds T M-tiles (T accumulators live in TMEM);
+//   * TMEM: 2 x T x BN = 512 columns, double buffered across super-tiles as before.
+struct ConvParams2 {
+  int c0_blocks, ctot_blocks;
+  int tiles_w, tiles_h, batch;
+  int n_tiles, num_tiles;
+  int H, W, cout, relu;
+  const float* bias;
+  const __nv_bfloat16* mask;
+};
+
+template <int BN, int T>
+struct ConvCfg2 {
+  static constexpr int kARows = 16 * T + 2;
+  static constexpr int kABytes = kARows * 1024;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kSA = (T == 4) ? 2 : 3;
+  static constexpr int kSB = BN == 64 ? 6 : (BN == 128 ? 5 : 4);
+  static constexpr int kStagingBytes = 2 * 16384;
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + kStagingBytes + 1024 + 1024;
+  static constexpr uint32_t kTmemCols = 2 * T * BN;
+  static_assert(kTmemCols == 512, "TMEM budget: 2 x T x BN must be 512 columns");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int BN, int T>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
+                        const __grid_constant__ CUtensorMap tmA1,
+                        const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmD, const ConvParams2 p) {
+  using Cfg = ConvCfg2<BN, T>;
+  constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + SA * Cfg::kABytes;
+  const uint32_t staging_base = b_base + SB * Cfg::kBBytes;
+  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
+  auto fullA = [&](int i) { return bar_base + 8u * i; };
+  auto emptyA = [&](int i) { return bar_base + 8u * (SA + i); };
+  auto fullB = [&](int i) { return bar_base + 8u * (2 * SA + i); };
+  auto emptyB = [&](int i) { return bar_base + 8u * (2 * SA + SB + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * SA + 2 * SB + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(fullA(i), 1);
+      mbar_init(emptyA(i), 1);
+    }
+    for (int i = 0; i < SB; ++i) {
+      mbar_init(fullB(i), 1);
+      mbar_init(emptyB(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int tile, int& b, int& h0, int& w0, int& n0) {
+    const int nt = tile % p.n_tiles;
+    int mt = tile / p.n_tiles;
+    const int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const int th = mt % p.tiles_h;
+    b = mt / p.tiles_h;
+    h0 = th * 16 * T;
+    w0 = tw * 8;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int b, h0, w0, n0;
+        decode(tile, b, h0, w0, n0);
+        for (int cb = 0; cb < p.ctot_blocks; ++cb) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(emptyA(sa), pa ^ 1u);
+            mbar_arrive_expect_tx(fullA(sa), Cfg::kABytes);
+            if (cb < p.c0_blocks)
+              tma_load_4d(a_base + sa * Cfg::kABytes, &tmA0, fullA(sa), cb * 64, w0 + s - 1, h0 - 1, b);
+            else
+              tma_load_4d(a_base + sa * Cfg::kABytes, &tmA1, fullA(sa), (cb - p.c0_blocks) * 64,
+                          w0 + s - 1, h0 - 1, b);
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(emptyB(sb), pb ^ 1u);
+              mbar_arrive_expect_tx(fullB(sb), Cfg::kBBytes);
+              tma_load_2d(b_base + sb * Cfg::kBBytes, &tmB, fullB(sb),
+                          ((r * 3 + s) * p.ctot_blocks + cb) * 64, n0);
+              if (++sb == SB) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer (one thread)
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (T * BN);
+        for (int cb = 0; cb < p.ctot_blocks; ++cb) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(fullA(sa), pa);
+            tc_fence_after();
+            const uint32_t a_addr = a_base + sa * Cfg::kABytes;
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(fullB(sb), pb);
+              tc_fence_after();
+              const uint32_t b_addr = b_base + sb * Cfg::kBBytes;
+              const uint32_t first = (cb | s | r) == 0 ? 1u : 0u;
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                const uint32_t at = a_addr + (16 * t + r) * 1024;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t adesc = umma_smem_desc_sw128(at + k * 32, 16, 1024);
+                  const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                  umma_bf16(d_tmem + t * BN, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+                }
+              }
+              umma_commit(emptyB(sb));
+              if (++sb == SB) { sb = 0; pb ^= 1u; }
+            }
+            umma_commit(emptyA(sa));
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // pixel within an M-tile == TMEM lane
+    const bool issuer = (threadIdx.x == 64);
+    const int ph = row >> 3, pw = row & 7;
+    uint32_t store_count = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int b, h0, w0, n0;
+      decode(tile, b, h0, w0, n0);
+      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const int h = h0 + 16 * t + ph, w = w0 + pw;
+        const bool inb = (h < p.H) && (w < p.W);
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 64; ++chunk) {
+          uint32_t v0[32], v1[32];
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)(q * 32) << 16) + buf * (T * BN) + t * BN + chunk * 64;
+          tmem_ld_32x32(taddr, v0);
+          tmem_ld_32x32(taddr + 32, v1);
+          tmem_ld_wait();
+          if (t == T - 1 && chunk == BN / 64 - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(buf));
+          }
+          const int cbase = n0 + chunk * 64;
+          const float* bptr = p.bias != nullptr ? p.bias + cbase : nullptr;
+          const uint4* mptr = nullptr;
+          if (p.mask != nullptr && inb)
+            mptr = reinterpret_cast<const uint4*>(
+                p.mask + ((size_t)(b * p.H + h) * p.W + w) * p.cout + cbase);
+          uint32_t pk0[16], pk1[16];
+          epilogue_half(v0, bptr, p.relu, mptr, pk0);
+          epilogue_half(v1, bptr ? bptr + 32 : nullptr, p.relu, mptr ? mptr + 4 : nullptr, pk1);
+          const uint32_t sbuf = staging_base + (store_count & 1u) * 16384u;
+          ++store_count;
+          if (issuer) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint8_t* srow = smem + (sbuf - base) + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) =
+                make_uint4(pk0[4 * j], pk0[4 * j + 1], pk0[4 * j + 2], pk0[4 * j + 3]);
+            *reinterpret_cast<uint4*>(srow + (((j + 4) ^ (row & 7)) << 4)) =
+                make_uint4(pk1[4 * j], pk1[4 * j + 1], pk1[4 * j + 2], pk1[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (issuer) {
+            if (h0 + 16 * t < p.H) tma_store_4d(&tmD, sbuf, cbase, w0, h0 + 16 * t, b);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int BN, int T>
+static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
+                        const CUtensorMap& dm, const ConvParams2& p, cudaStream_t st) {
+  using Cfg = ConvCfg2<BN, T>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  conv3x3_igemm_v2_kernel<BN, T><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
+  WU_CHECK_LAUNCH("conv3x3_igemm_v2_kernel");
+  return WU_OK;
+}
+
+// WU_CONV_IMPL: 0 / unset = per-shape choice, 1 = v1 everywhere, 2 = v2 everywhere (read once).
+static int conv_impl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WU_CONV_IMPL");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+  }
+  return v;
 }
 
 static int ilog2(int v) {
@@ -628,6 +900,41 @@ extern "C" int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int 
   WU_REQUIRE(cout > 0 && cout % 64 == 0 && cout != 192 && (cout <= 256 || cout % 256 == 0),
              "wu_conv3x3_fprop: cout=%d must be 64, 128 or a multiple of 256", cout);
   const int bn = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
+  if (conv_impl() == 2 || (conv_impl() == 0 && bn < 256)) {
+    const int T = bn == 64 ? 4 : (bn == 128 ? 2 : 1);
+    ConvParams2 q;
+    q.c0_blocks = c0 / 64;
+    q.ctot_blocks = (c0 + c1) / 64;
+    q.tiles_w = (W + 7) / 8;
+    q.tiles_h = (H + 16 * T - 1) / (16 * T);
+    q.batch = B;
+    q.n_tiles = cout / bn;
+    const long long nt2 = (long long)B * q.tiles_w * q.tiles_h * q.n_tiles;
+    WU_REQUIRE(nt2 < (1LL << 31), "wu_conv3x3_fprop: too many tiles");
+    q.num_tiles = (int)nt2;
+    q.H = H;
+    q.W = W;
+    q.cout = cout;
+    q.relu = relu;
+    q.bias = bias;
+    q.mask = (const __nv_bfloat16*)relu_mask_src;
+    CUtensorMap a0, a1, bm, dm;
+    int rc;
+    if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, 8, 16 * T + 2)) != WU_OK) return rc;
+    if (c1 > 0) {
+      if ((rc = make_act_tmap(&a1, src1, B, H, W, c1, c1, 8, 16 * T + 2)) != WU_OK) return rc;
+    } else {
+      a1 = a0;
+    }
+    if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * (c0 + c1), bn)) != WU_OK) return rc;
+    if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, 8, 16)) != WU_OK) return rc;
+    cudaStream_t st2 = (cudaStream_t)stream;
+    switch (bn) {
+      case 64: return launch_conv2<64, 4>(a0, a1, bm, dm, q, st2);
+      case 128: return launch_conv2<128, 2>(a0, a1, bm, dm, q, st2);
+      default: return launch_conv2<256, 1>(a0, a1, bm, dm, q, st2);
+    }
+  }
   ConvParams p;
   pick_box(H, W, 128, &p.bw, &p.bh);
   p.log2_bw = ilog2(p.bw);
