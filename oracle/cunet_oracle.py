@@ -52,13 +52,17 @@ def _qw(w, on):
     return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach() if on else w
 
 
-def double_conv(sd, name, x, q=False, q_first=True):
+def double_conv(sd, name, x, q=False, q_first=True, tap=None):
     """nets.py:18-24: conv3x3(pad 1) -> ReLU -> conv3x3(pad 1) -> ReLU.
     q: emulate the CUDA path's storage precision (bf16 weights and activations, fp32 accumulate);
-    q_first=False keeps the first convolution's weights in fp32 (the K=27 image layer does)."""
+    q_first=False keeps the first convolution's weights in fp32 (the K=27 image layer does).
+    tap: optional callable(name_suffix, tensor) -> tensor applied to both activations."""
+    tap = tap or (lambda k, v: v)
     x = _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.0.weight"], q and q_first), sd[f"{name}.0.bias"],
                            padding=1)), q)
-    return _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.2.weight"], q), sd[f"{name}.2.bias"], padding=1)), q)
+    x = tap(f"{name}.a", x)
+    x = _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.2.weight"], q), sd[f"{name}.2.bias"], padding=1)), q)
+    return tap(f"{name}.b", x)
 
 
 def adain(sd, name, x, c, eps=EPS):
@@ -91,30 +95,48 @@ def dropout(x, mask, train, p=P_DROP):
     return x * (keep / (1 - p)), keep
 
 
-def forward(sd, x, c, train=False, masks=None, p=P_DROP, collect=None, emulate_bf16=False):
+# name of each activation in the CUDA path's bookkeeping (weather-unet_b200/_generator.py)
+ACT_NAMES = {"dconv_down1.a": "a1", "dconv_down1.b": "conv1", "dconv_down2.a": "d2a",
+             "dconv_down2.b": "conv2", "dconv_down3.a": "d3a", "dconv_down3.b": "conv3",
+             "dconv_down4.a": "d4a", "dconv_down4.b": "x4", "dconv_up3.a": "up3a",
+             "dconv_up3.b": "up3b", "dconv_up2.a": "up2a", "dconv_up2.b": "up2b",
+             "dconv_up1.a": "up1a", "dconv_up1.b": "up1b"}
+
+
+def forward(sd, x, c, train=False, masks=None, p=P_DROP, collect=None, emulate_bf16=False,
+            override=None):
     """cunet.py:43-82.  `masks`: optional 3 uint8 NHWC keep masks (sites adain3, adain2, adain1).
     `collect`: optional dict filled with named intermediate activations (NCHW) and drawn masks.
     `emulate_bf16`: NOT the reference's arithmetic — the same dataflow with values rounded to bf16
-    wherever the CUDA path stores bf16 (conv weights, activations, activation gradients), so that
-    ReLU masks / pooling arg-maxes agree and kernel parity can be checked tightly."""
+    wherever the CUDA path stores bf16 (conv weights, activations, activation gradients).
+    `override`: dict name -> NCHW tensor; each named activation takes the given VALUE while keeping
+    its local derivative ("teacher forcing"), so that ReLU masks / pooling arg-maxes of a backward
+    pass agree with the run the values came from and gradient parity can be checked tightly."""
     q = emulate_bf16
     masks = masks or (None, None, None)
-    keep = lambda k, v: collect.__setitem__(k, v) if collect is not None else None  # noqa: E731
-    conv1 = double_conv(sd, "dconv_down1", x, q, q_first=False)
-    conv2 = double_conv(sd, "dconv_down2", F.max_pool2d(conv1, 2), q)
-    conv3 = double_conv(sd, "dconv_down3", F.max_pool2d(conv2, 2), q)
-    h = double_conv(sd, "dconv_down4", F.max_pool2d(conv3, 2), q)
-    keep("conv1", conv1), keep("conv2", conv2), keep("conv3", conv3), keep("x4", h)
+
+    def tap(k, v):
+        k = ACT_NAMES.get(k, k)
+        if override is not None and k in override:
+            v = v + (override[k].to(v.dtype) - v).detach()
+        if collect is not None:
+            collect[k] = v
+        return v
+
+    conv1 = double_conv(sd, "dconv_down1", x, q, q_first=False, tap=tap)
+    conv2 = double_conv(sd, "dconv_down2", F.max_pool2d(conv1, 2), q, tap=tap)
+    conv3 = double_conv(sd, "dconv_down3", F.max_pool2d(conv2, 2), q, tap=tap)
+    h = double_conv(sd, "dconv_down4", F.max_pool2d(conv3, 2), q, tap=tap)
     for i, (ad, up, skip) in enumerate((("adain3", "dconv_up3", conv3),
                                         ("adain2", "dconv_up2", conv2),
                                         ("adain1", "dconv_up1", conv1))):
         z = adain(sd, ad, h, c)
         h = upsample(_RoundGradBF16.apply(z) if q else z)
         h, m = dropout(h, masks[i], train, p)
-        h = _q(h, q)
-        keep(f"u{3 - i}", h), keep(f"mask{3 - i}", m)
-        h = double_conv(sd, up, torch.cat([h, skip], dim=1), q)  # concat order [x, skip] (cunet.py:62)
-        keep(f"up{3 - i}b", h)
+        h = tap(f"u{3 - i}", _q(h, q))
+        if collect is not None:
+            collect[f"mask{3 - i}"] = m
+        h = double_conv(sd, up, torch.cat([h, skip], dim=1), q, tap=tap)  # [x, skip] (cunet.py:62)
     out = F.conv2d(h, sd["conv_last.weight"], sd["conv_last.bias"])
     return torch.tanh(out)
 

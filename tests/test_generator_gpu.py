@@ -86,11 +86,12 @@ def test_against_oracle(cuda, B, H, W, nc, train):
     (y * gy).sum().backward()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
 
-    def run_oracle(emulate, autocast=False):
+    def run_oracle(emulate, autocast=False, override=None):
         col = {}
         leaf = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            y_ref = orc.forward(leaf, x, c, train=train, masks=masks, collect=col, emulate_bf16=emulate)
+            y_ref = orc.forward(leaf, x, c, train=train, masks=masks, collect=col, emulate_bf16=emulate,
+                                override=override)
         (y_ref.float() * gy).sum().backward()
         return y_ref.float().detach(), col, {k: v.grad for k, v in leaf.items() if v.grad is not None}
 
@@ -102,9 +103,8 @@ def test_against_oracle(cuda, B, H, W, nc, train):
     for k in ("conv1", "conv2", "conv3", "x4", "up3b", "up2b", "up1b"):
         assert rel(acts[k].float().permute(0, 3, 1, 2), col32[k]) < 3e-2, f"activation {k}"
     assert (y.detach() - y32).abs().max().item() < 3e-2
-    # (2) bf16-emulating oracle (same dataflow, values rounded where the kernels store bf16):
-    # tight kernel parity, forward and all 36 gradients
-    yq, colq, gq = run_oracle(True)
+    # (2) bf16-emulating oracle (same dataflow, values rounded where the kernels store bf16)
+    yq, colq, _ = run_oracle(True)
     act_q = {k: rel(acts[k].float().permute(0, 3, 1, 2), colq[k])
              for k in ("conv1", "conv2", "conv3", "x4", "up3b", "up2b", "up1b")}
     print("activations vs bf16 oracle:", {k: f"{v:.2e}" for k, v in act_q.items()})
@@ -112,7 +112,17 @@ def test_against_oracle(cuda, B, H, W, nc, train):
         # one-ulp bf16 differences (accumulation order) propagate: 3e-3 per layer, 2e-2 at depth 14
         assert v < 2e-2, f"activation {k} (bf16 oracle): {v:.3e}"
     assert (y.detach() - yq).abs().max().item() < 1e-2
-    # (3) stock PyTorch autocast(bf16) of the oracle: the error band bf16 has on this network
+    # (3) gradients.  End to end, bf16 storage perturbs ReLU masks / arg-maxes and this randomly
+    # initialised network amplifies that to 10-35 % rel-L2 on deep layers — for a stock
+    # torch.autocast(bf16) run of the oracle just as much (the "band" below).  The kernel-chain
+    # check therefore teacher-forces the oracle with OUR forward activations (same masks), once in
+    # fp32 (g_tf) and once with bf16-rounded activation gradients / weights like the kernels
+    # (g_tfq).  rel(g_tfq, g_tf) is the noise bf16 gradient storage alone causes; ours must stay
+    # within 1.5x that + 2e-2 of g_tf, and point the same way (cos >= 0.99).
+    forced = {k: v.float().permute(0, 3, 1, 2) for k, v in acts.items()
+              if k not in ("x", "c", "y", "p1", "p2", "p3")}
+    _, _, gtf = run_oracle(False, override=forced)
+    _, _, gtfq = run_oracle(True, override=forced)
     _, _, gac = run_oracle(False, autocast=True)
     report = []
     for name, p in net.named_parameters():
@@ -120,18 +130,21 @@ def test_against_oracle(cuda, B, H, W, nc, train):
             assert p.grad is None
             continue
         gm = p.grad.float().flatten()
-        r_q, r_32 = rel(gm, gq[name].flatten()), rel(gm, g32[name].flatten())
+        r_tf, r_32 = rel(gm, gtf[name].flatten()), rel(gm, g32[name].flatten())
+        r_noise = rel(gtfq[name].flatten(), gtf[name].flatten())
         r_ac = rel(gac[name].flatten(), g32[name].flatten())
-        cos_q = torch.nn.functional.cosine_similarity(gm, gq[name].flatten().float(), dim=0).item()
-        report.append((name, r_q, cos_q, r_32, r_ac))
-    lines = [f"{name:26s} vs bf16-oracle rel-L2 {r_q:.3e} cos {cos_q:.5f} | vs fp32 {r_32:.3e} "
-             f"(autocast {r_ac:.3e})" for name, r_q, cos_q, r_32, r_ac in report]
+        cos_tf = torch.nn.functional.cosine_similarity(gm, gtf[name].flatten().float(), dim=0).item()
+        report.append((name, r_tf, cos_tf, r_noise, r_32, r_ac))
+    lines = [f"{name:24s} teacher-forced: ours {r_tf:.3e} cos {cos_tf:.5f} (bf16-storage noise {r_noise:.3e})"
+             f" | end-to-end vs fp32: ours {r_32:.3e} (autocast-bf16 {r_ac:.3e})"
+             for name, r_tf, cos_tf, r_noise, r_32, r_ac in report]
     print("\n".join(lines))
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/grad_parity_B{B}_H{H}_W{W}_train{int(train)}.txt", "w") as f:
         f.write("\n".join(lines) + "\n")
-    for name, r_q, cos_q, r_32, r_ac in report:
-        assert r_q < 6e-2 and cos_q > 0.998, f"{name}: vs bf16 oracle rel-L2 {r_q:.3e} cos {cos_q:.5f}"
+    for name, r_tf, cos_tf, r_noise, r_32, r_ac in report:
+        assert r_tf < 1.5 * r_noise + 2e-2 and cos_tf > 0.99, \
+            f"{name}: teacher-forced rel-L2 {r_tf:.3e} (noise {r_noise:.3e}) cos {cos_tf:.5f}"
         assert r_32 < 1.3 * r_ac + 2e-2, f"{name}: vs fp32 {r_32:.3e}, autocast-bf16 band {r_ac:.3e}"
 
 

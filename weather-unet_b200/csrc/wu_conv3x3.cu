@@ -753,6 +753,230 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad, v2: operand reuse in shared memory
+// ------------------------------------------------------------------------------------------------
+// v1 gives every CTA two (tap, channel block) atoms, so the dY tile is re-fetched for each pair
+// and every X tile once per tap (ncu: L2 -> SMEM bound, tensor pipe ~22 %).  v2 gives a CTA up to
+// NC "copies" = (column shift s, channel block cb) pairs; one TMA box (64 ch, 8 px, 8+2 rows) per
+// copy and pixel tile serves the three taps r = 0..2 of that column shift through start-address
+// offsets of r KiB (8 pixels x 128 B: 1024-byte aligned), and one dY tile feeds all 3*NC atoms:
+//   M-blocks (128 accumulator lanes = two 64-row atoms) per CTA:
+//     [copy c: r=0 | r=1]            atoms 1 KiB apart   -> LBO = 1024      (one per copy)
+//     [r=2 of copy c | r=2 of c+1]   atoms one copy apart -> LBO = 10 KiB   (one per copy pair)
+//   TMEM columns = (NC + ceil(NC/2)) * BN  (NC = 5, BN = 64: 512;  NC = 2, BN = 128: 384).
+// A lone r=2 atom is issued as an M=128 block whose upper half is never read back.
+struct WgradParams2 {
+  int c0_blocks, ctot_blocks;
+  int copies;  // 3 * ctot_blocks
+  int groups;  // ceil(copies / NC)
+  int n_tiles, splits;
+  int tiles_w, tiles_h, batch;
+  int pix_tiles;
+  int cout, cin_total;
+  float* partial;  // [splits][9*cin_total][cout]
+};
+
+template <int BN, int NC>
+struct WgradCfg2 {
+  static constexpr int kCopyBytes = 10 * 1024;  // (8+2) rows x 8 px x 128 B
+  static constexpr int kAtomBytes = 64 * 128;
+  static constexpr int kABytes = NC * kCopyBytes;
+  static constexpr int kBBytes = (BN / 64) * kAtomBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (220 * 1024) / kStageBytes > 6 ? 6 : (220 * 1024) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+  static constexpr int kBlocks = NC + (NC + 1) / 2;
+  static constexpr uint32_t kTmemColsUsed = kBlocks * BN;
+  static constexpr uint32_t kTmemCols = kTmemColsUsed <= 256 ? 256 : 512;
+  static_assert(kTmemColsUsed <= 512, "TMEM budget");
+  static_assert(kStages >= 3, "pipeline depth");
+  static_assert(kStageBytes % 1024 == 0, "stage alignment");
+};
+
+template <int BN, int NC>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
+                        const __grid_constant__ CUtensorMap tmX1,
+                        const __grid_constant__ CUtensorMap tmY, const WgradParams2 p) {
+  using Cfg = WgradCfg2<BN, NC>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar_base = base + S * Cfg::kStageBytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (S + i); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // blockIdx.x -> (copy group, n tile, split)
+  int id = blockIdx.x;
+  const int z = id % p.splits;
+  id /= p.splits;
+  const int nt = id % p.n_tiles;
+  const int grp = id / p.n_tiles;
+  const int n0 = nt * BN;
+  const int g0 = grp * NC;                                       // first global copy id
+  const int nc = (p.copies - g0) < NC ? (p.copies - g0) : NC;    // copies of this CTA
+  const int pt_begin = (int)(((long long)p.pix_tiles * z) / p.splits);
+  const int pt_end = (int)(((long long)p.pix_tiles * (z + 1)) / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX0);
+    tma_prefetch_desc(&tmX1);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(nc * Cfg::kCopyBytes + Cfg::kBBytes);
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        int m = pt;
+        const int tw = m % p.tiles_w;
+        m /= p.tiles_w;
+        const int th = m % p.tiles_h;
+        const int b = m / p.tiles_h;
+        const int w0 = tw * 8, h0 = th * 8;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t fb = full_bar(stage);
+        mbar_arrive_expect_tx(fb, tx);
+        const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+        const uint32_t b_dst = a_dst + Cfg::kABytes;
+        for (int c = 0; c < nc; ++c) {
+          const int g = g0 + c;
+          const int s = g / p.ctot_blocks, cb = g - s * p.ctot_blocks;
+          if (cb < p.c0_blocks)
+            tma_load_4d(a_dst + c * Cfg::kCopyBytes, &tmX0, fb, cb * 64, w0 + s - 1, h0 - 1, b);
+          else
+            tma_load_4d(a_dst + c * Cfg::kCopyBytes, &tmX1, fb, (cb - p.c0_blocks) * 64, w0 + s - 1,
+                        h0 - 1, b);
+        }
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(b_dst + j * Cfg::kAtomBytes, &tmY, fb, n0 + j * 64, w0, h0, b);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
+      const int npair = (nc + 1) >> 1;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+        const uint32_t acc = pt != pt_begin ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 pixels = 2 rows of 8 = 2 KiB)
+          const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, Cfg::kAtomBytes, 1024);
+          for (int c = 0; c < nc; ++c) {  // [r=0 | r=1] of copy c
+            const uint64_t adesc =
+                umma_smem_desc_sw128(a_addr + c * Cfg::kCopyBytes + k * 2048, 1024, 1024);
+            umma_bf16(tmem_base + c * BN, adesc, bdesc, idesc, (acc | (uint32_t)k) != 0 ? 1u : 0u);
+          }
+          for (int j = 0; j < npair; ++j) {  // [r=2 of copy 2j | r=2 of copy 2j+1]
+            const uint32_t lbo = (2 * j + 1 < nc) ? (uint32_t)Cfg::kCopyBytes : 1024u;
+            const uint64_t adesc = umma_smem_desc_sw128(
+                a_addr + 2 * j * Cfg::kCopyBytes + 2 * 1024 + k * 2048, lbo, 1024);
+            umma_bf16(tmem_base + (nc + j) * BN, adesc, bdesc, idesc,
+                      (acc | (uint32_t)k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int half = row >> 6, r64 = row & 63;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int nblocks = nc + ((nc + 1) >> 1);
+#pragma unroll 1
+    for (int blk = 0; blk < nblocks; ++blk) {
+      // which (tap row r, copy c) does this lane's atom hold?
+      int r, c;
+      if (blk < nc) {
+        c = blk;
+        r = half;
+      } else {
+        c = 2 * (blk - nc) + half;
+        r = 2;
+      }
+      const bool valid = c < nc;
+      const int g = g0 + (valid ? c : 0);
+      const int s = g / p.ctot_blocks, cb = g - s * p.ctot_blocks;
+      const int tap = r * 3 + s;
+      float* out = p.partial +
+                   ((size_t)z * 9 * p.cin_total + (size_t)tap * p.cin_total + cb * 64 + r64) * p.cout + n0;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + blk * BN + chunk * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(out + chunk * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int BN, int NC>
+static int launch_wgrad2(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& ym,
+                         const WgradParams2& p, int grid, cudaStream_t st) {
+  using Cfg = WgradCfg2<BN, NC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_v2_kernel<BN, NC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  conv3x3_wgrad_v2_kernel<BN, NC><<<grid, 192, Cfg::kSmemBytes, st>>>(x0, x1, ym, p);
+  WU_CHECK_LAUNCH("conv3x3_wgrad_v2_kernel");
+  return WU_OK;
+}
+
 // dw[co][ci][tap] = sum_z partial[z][tap*cin + ci][co]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                     int splits, int cin, int cout) {
@@ -826,10 +1050,37 @@ struct WgradPlan {
   int bn, n_tiles, pairs, atoms, splits, bw, bh, tiles_w, tiles_h, pix_tiles;
   size_t partial_bytes, bias_bytes;
   int bias_blocks;
+  int v2, nc, groups;
 };
 
 static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
   WgradPlan pl;
+  pl.v2 = conv_impl() != 1;
+  if (pl.v2) {
+    pl.bn = cout >= 128 ? 128 : 64;
+    pl.nc = pl.bn == 64 ? 5 : 2;
+    pl.n_tiles = cout / pl.bn;
+    const int copies = 3 * (cin_total / 64);
+    pl.groups = (copies + pl.nc - 1) / pl.nc;
+    pl.atoms = 9 * (cin_total / 64);
+    pl.pairs = 0;
+    pl.bw = 8;
+    pl.bh = 8;
+    pl.tiles_w = (W + 7) / 8;
+    pl.tiles_h = (H + 7) / 8;
+    pl.pix_tiles = B * pl.tiles_w * pl.tiles_h;
+    const int tiles = pl.groups * pl.n_tiles;
+    int splits = (2 * 148 + tiles - 1) / tiles;
+    if (splits > pl.pix_tiles) splits = pl.pix_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > 148) splits = 148;
+    pl.splits = splits;
+    pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
+    pl.bias_blocks = 296;
+    pl.bias_bytes = (size_t)pl.bias_blocks * cout * sizeof(float);
+    return pl;
+  }
+  pl.nc = pl.groups = 0;
   pl.bn = cout >= 256 ? 256 : cout;  // 64 / 128 / 256
   pl.n_tiles = cout / pl.bn;
   pl.atoms = 9 * (cin_total / 64);
@@ -971,6 +1222,32 @@ extern "C" int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int 
   }
 }
 
+// split-K fold into the reference layout + bias gradient
+static int wgrad_finish(const float* partial, float* dw, float* db, const void* dy, void* workspace,
+                        const WgradPlan& pl, int cin, int cout, int B, int H, int W,
+                        cudaStream_t st) {
+  {
+    const long long total = 9LL * cin * cout;
+    int g = (int)((total + 255) / 256);
+    if (g > 148 * 16) g = 148 * 16;
+    wgrad_reduce_kernel<<<g, 256, 0, st>>>(partial, dw, pl.splits, cin, cout);
+    WU_CHECK_LAUNCH("wgrad_reduce_kernel");
+  }
+  if (db != nullptr) {
+    float* bpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.partial_bytes);
+    const long long npix = (long long)B * H * W;
+    const int lanes = cout / 8;
+    const int groups = 256 / lanes;
+    WU_REQUIRE(groups >= 1, "wu_conv3x3_wgrad: cout=%d too wide for the bias-grad kernel", cout);
+    bias_grad_partial_kernel<<<pl.bias_blocks, 256, groups * cout * sizeof(float), st>>>(
+        (const __nv_bfloat16*)dy, bpart, npix, cout);
+    WU_CHECK_LAUNCH("bias_grad_partial_kernel");
+    bias_grad_final_kernel<<<(cout + 127) / 128, 128, 0, st>>>(bpart, db, pl.bias_blocks, cout);
+    WU_CHECK_LAUNCH("bias_grad_final_kernel");
+  }
+  return WU_OK;
+}
+
 extern "C" size_t wu_conv3x3_wgrad_workspace_bytes(int cin_total, int cout, int B, int H, int W) {
   if (cin_total <= 0 || cout <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
   const WgradPlan pl = plan_wgrad(cin_total, cout, B, H, W);
@@ -993,6 +1270,37 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
              "wu_conv3x3_wgrad: workspace %zu < required %zu", workspace_bytes,
              pl.partial_bytes + pl.bias_bytes);
   WU_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "wu_conv3x3_wgrad: workspace unaligned");
+  if (pl.v2) {
+    WgradParams2 q;
+    q.c0_blocks = c0 / 64;
+    q.ctot_blocks = cin / 64;
+    q.copies = 3 * q.ctot_blocks;
+    q.groups = pl.groups;
+    q.n_tiles = pl.n_tiles;
+    q.splits = pl.splits;
+    q.tiles_w = pl.tiles_w;
+    q.tiles_h = pl.tiles_h;
+    q.batch = B;
+    q.pix_tiles = pl.pix_tiles;
+    q.cout = cout;
+    q.cin_total = cin;
+    q.partial = reinterpret_cast<float*>(workspace);
+    CUtensorMap x0, x1, ym;
+    int rc;
+    if ((rc = make_act_tmap(&x0, src0, B, H, W, c0, c0, 8, 10)) != WU_OK) return rc;
+    if (c1 > 0) {
+      if ((rc = make_act_tmap(&x1, src1, B, H, W, c1, c1, 8, 10)) != WU_OK) return rc;
+    } else {
+      x1 = x0;
+    }
+    if ((rc = make_act_tmap(&ym, dy, B, H, W, cout, cout, 8, 8)) != WU_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = pl.groups * pl.n_tiles * pl.splits;
+    if (pl.bn == 64) rc = launch_wgrad2<64, 5>(x0, x1, ym, q, grid, st);
+    else rc = launch_wgrad2<128, 2>(x0, x1, ym, q, grid, st);
+    if (rc != WU_OK) return rc;
+    return wgrad_finish(q.partial, dw, db, dy, workspace, pl, cin, cout, B, H, W, st);
+  }
   WgradParams p;
   p.c0_blocks = c0 / 64;
   p.ctot_blocks = cin / 64;
@@ -1025,24 +1333,5 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     default: rc = launch_wgrad<256>(x0, x1, ym, p, grid, st); break;
   }
   if (rc != WU_OK) return rc;
-  {
-    const long long total = 9LL * cin * cout;
-    int g = (int)((total + 255) / 256);
-    if (g > 148 * 16) g = 148 * 16;
-    wgrad_reduce_kernel<<<g, 256, 0, st>>>(p.partial, dw, pl.splits, cin, cout);
-    WU_CHECK_LAUNCH("wgrad_reduce_kernel");
-  }
-  if (db != nullptr) {
-    float* bpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.partial_bytes);
-    const long long npix = (long long)B * H * W;
-    const int lanes = cout / 8;
-    const int groups = 256 / lanes;
-    WU_REQUIRE(groups >= 1, "wu_conv3x3_wgrad: cout=%d too wide for the bias-grad kernel", cout);
-    bias_grad_partial_kernel<<<pl.bias_blocks, 256, groups * cout * sizeof(float), st>>>(
-        (const __nv_bfloat16*)dy, bpart, npix, cout);
-    WU_CHECK_LAUNCH("bias_grad_partial_kernel");
-    bias_grad_final_kernel<<<(cout + 127) / 128, 128, 0, st>>>(bpart, db, pl.bias_blocks, cout);
-    WU_CHECK_LAUNCH("bias_grad_final_kernel");
-  }
-  return WU_OK;
+  return wgrad_finish(p.partial, dw, db, dy, workspace, pl, cin, cout, B, H, W, st);
 }
