@@ -97,6 +97,7 @@ class _CUNetFn(torch.autograd.Function):
         ctx.sts = (st3, st2, st1)
         ctx.params = P
         ctx.packed = packed
+        ctx.grad_sink = opts.get("grad_sink")
         if opts.get("keep_acts") is not None:
             opts["keep_acts"].update(ctx.acts)
         return y
@@ -106,7 +107,21 @@ class _CUNetFn(torch.autograd.Function):
         A, P, packed = ctx.acts, ctx.params, ctx.packed
         st3, st2, st1 = ctx.sts
         c = A["c"]
-        G = {}
+        sink = ctx.grad_sink
+
+        class _Grads(dict):
+            """Parameter gradients as they are produced.  In data-parallel mode each one is written
+            straight into its flat all-reduce bucket and reported ready, so the bucket's NCCL
+            all-reduce starts while the rest of the backward pass is still running."""
+
+            def __setitem__(self, name, t):
+                if sink is not None and t is not None and name in sink.where:
+                    sink.grad_view(name).copy_(t.view_as(P[name]))
+                    sink.ready(name)
+                    t = None
+                dict.__setitem__(self, name, t)
+
+        G = _Grads()
 
         def wd(name):
             return packed.get(name, P[name])[1]
@@ -163,7 +178,8 @@ class _CUNetFn(torch.autograd.Function):
         ctx.acts = None
         grads = []
         for i, n in enumerate(PARAM_NAMES):
-            grads.append(G[n].view_as(P[n]) if ctx.needs_input_grad[3 + i] else None)
+            g = G[n]
+            grads.append(g.view_as(P[n]) if (g is not None and ctx.needs_input_grad[3 + i]) else None)
         # no gradient for the image or the condition (the reference never asks for them:
         # t_cls_train.py:242,272 differentiates w.r.t. the generator's parameters only)
         return (None, None, None) + tuple(grads)
@@ -203,5 +219,6 @@ def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=Non
     params = [module.get_parameter(n) for n in PARAM_NAMES]
     opts = dict(training=training, p=module.dropout.p, masks=masks, seed=seed,
                 eps=(module.adain3.eps, module.adain2.eps, module.adain1.eps),
-                packed=module._packed, keep_acts=keep_acts)
+                packed=module._packed, keep_acts=keep_acts,
+                grad_sink=getattr(module, "_grad_sink", None))
     return _CUNetFn.apply(x, c, opts, *params)

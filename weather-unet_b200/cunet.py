@@ -58,6 +58,7 @@ class Conditional_UNet(nn.Module):
         self.conv_last = nn.Conv2d(64, 3, 1)
         self.activation = nn.Tanh()
         self._packed = PackedWeights()  # derived bf16 weights: not parameters, not persistent
+        self._grad_sink = None  # data-parallel gradient buckets (train_step.GradBuckets), if any
 
     def forward(self, x, c, dropout_masks=None, seed=None, _keep_acts=None):
         """x: (B, 3, H, W) float in [-1, 1], H and W divisible by 8; c: (B, num_classes) float.

@@ -46,7 +46,7 @@ class GradBuckets:
                 off += p.numel()
             self.flat.append(flat)
         self.pending = [len(b) for b in self.buckets]
-        self.works = []
+        self.launched = [False] * len(self.buckets)
         dev = self.flat[0].device if self.flat else None
         self.comm_stream = torch.cuda.Stream(device=dev) if (dev is not None and dev.type == "cuda") else None
         self._hooks = []
@@ -62,6 +62,7 @@ class GradBuckets:
         for f in self.flat:
             f.zero_()
         self.pending = [len(b) for b in self.buckets]
+        self.launched = [False] * len(self.buckets)
 
     def grad_view(self, name):
         bi = self.where[name]
@@ -76,22 +77,31 @@ class GradBuckets:
         if bi is None:
             return
         self.pending[bi] -= 1
-        if self.pending[bi] == 0 and self.world > 1:
-            flat = self.flat[bi]
-            if self.comm_stream is not None:
-                self.comm_stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self.comm_stream):
-                    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-                    flat.div_(self.world)
-            else:  # CPU / gloo (tests)
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        if self.launched[bi] or self.world == 1:
+            return
+        self.launched[bi] = True
+        flat = self.flat[bi]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
                 flat.div_(self.world)
+        else:  # CPU / gloo (tests)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
 
     def finish(self):
-        """Make the compute stream wait for the outstanding reductions (call before optimizer.step)."""
+        """Reduce buckets that never completed (a parameter without gradient this pass — the same
+        on every rank, so the collective order still matches), then make the compute stream wait
+        for the outstanding reductions.  Call before optimizer.step()."""
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
         if self.comm_stream is not None and self.world > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        self.pending = [len(b) for b in self.buckets]
 
 
 class GDTrainStep:
