@@ -106,6 +106,42 @@ __device__ __forceinline__ void epilogue_half(uint32_t (&v)[32], const float* bi
   }
 }
 
+// Same, with the ReLU-gradient mask already in registers (prefetched while the MMAs were running).
+__device__ __forceinline__ void epilogue_half_r(uint32_t (&v)[32], const float* bias, int relu,
+                                                bool use_mask, const uint4* mreg, uint32_t (&pk)[16]) {
+  if (bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j));
+      v[j + 0] = __float_as_uint(__uint_as_float(v[j + 0]) + bv.x);
+      v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + bv.y);
+      v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + bv.z);
+      v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + bv.w);
+    }
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+  if (use_mask) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t mm[4] = {mreg[j].x, mreg[j].y, mreg[j].z, mreg[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t lo = mm[e] & 0xFFFFu, hi = mm[e] >> 16;
+        uint32_t keep = 0;
+        if (lo != 0 && (lo & 0x8000u) == 0) keep |= 0x0000FFFFu;  // bf16 value > 0
+        if (hi != 0 && (hi & 0x8000u) == 0) keep |= 0xFFFF0000u;
+        pk[4 * j + e] &= keep;
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
@@ -481,7 +517,25 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int row = q * 32 + lane;  // pixel within an M-tile == TMEM lane
     const bool issuer = (threadIdx.x == 64);
     const int ph = row >> 3, pw = row & 7;
+    constexpr int NCH = BN / 64;
     uint32_t store_count = 0;
+    // ReLU-gradient mask of the next (tile, t, chunk) is fetched one step ahead so that its L2
+    // latency hides behind the TMEM drain / staging of the current one
+    uint4 mk[8];
+    bool mk_ok = false;
+    auto fetch_mask = [&](int tile, int t, int chunk, uint4 (&m)[8]) -> bool {
+      if (p.mask == nullptr || tile >= p.num_tiles) return false;
+      int b, h0, w0, n0;
+      decode(tile, b, h0, w0, n0);
+      const int h = h0 + 16 * t + ph, w = w0 + pw;
+      if (h >= p.H || w >= p.W) return false;
+      const uint4* mp = reinterpret_cast<const uint4*>(
+          p.mask + ((size_t)(b * p.H + h) * p.W + w) * p.cout + n0 + chunk * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = __ldg(mp + j);
+      return true;
+    };
+    mk_ok = fetch_mask(blockIdx.x, 0, 0, mk);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -491,29 +545,31 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        const int h = h0 + 16 * t + ph, w = w0 + pw;
-        const bool inb = (h < p.H) && (w < p.W);
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 64; ++chunk) {
+        for (int chunk = 0; chunk < NCH; ++chunk) {
+          uint4 nx[8];
+          bool nx_ok;
+          if (chunk + 1 < NCH) nx_ok = fetch_mask(tile, t, chunk + 1, nx);
+          else if (t + 1 < T) nx_ok = fetch_mask(tile, t + 1, 0, nx);
+          else nx_ok = fetch_mask(tile + gridDim.x, 0, 0, nx);
           uint32_t v0[32], v1[32];
           const uint32_t taddr =
               tmem_base + ((uint32_t)(q * 32) << 16) + buf * (T * BN) + t * BN + chunk * 64;
           tmem_ld_32x32(taddr, v0);
           tmem_ld_32x32(taddr + 32, v1);
           tmem_ld_wait();
-          if (t == T - 1 && chunk == BN / 64 - 1) {
+          if (t == T - 1 && chunk == NCH - 1) {
             tc_fence_before();
             mbar_arrive(tempty_bar(buf));
           }
           const int cbase = n0 + chunk * 64;
           const float* bptr = p.bias != nullptr ? p.bias + cbase : nullptr;
-          const uint4* mptr = nullptr;
-          if (p.mask != nullptr && inb)
-            mptr = reinterpret_cast<const uint4*>(
-                p.mask + ((size_t)(b * p.H + h) * p.W + w) * p.cout + cbase);
           uint32_t pk0[16], pk1[16];
-          epilogue_half(v0, bptr, p.relu, mptr, pk0);
-          epilogue_half(v1, bptr ? bptr + 32 : nullptr, p.relu, mptr ? mptr + 4 : nullptr, pk1);
+          epilogue_half_r(v0, bptr, p.relu, mk_ok, mk, pk0);
+          epilogue_half_r(v1, bptr ? bptr + 32 : nullptr, p.relu, mk_ok, mk + 4, pk1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mk[j] = nx[j];
+          mk_ok = nx_ok;
           const uint32_t sbuf = staging_base + (store_count & 1u) * 16384u;
           ++store_count;
           if (issuer) tma_store_wait_read<1>();
@@ -1004,8 +1060,22 @@ bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict
   const int g = threadIdx.x / lanes, l = threadIdx.x % lanes;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (g < groups) {
-    for (long long px = (long long)blockIdx.x * groups + g; px < npix;
-         px += (long long)gridDim.x * groups) {
+    const long long stride = (long long)gridDim.x * groups;
+    long long px = (long long)blockIdx.x * groups + g;
+    for (; px + 3 * stride < npix; px += 4 * stride) {  // four independent 16-byte loads in flight
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = __ldg(reinterpret_cast<const uint4*>(dy + (px + u * stride) * C) + l);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x);
+        acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
+        acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z);
+        acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
+      }
+    }
+    for (; px < npix; px += stride) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + px * C) + l);
       acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x);
       acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
@@ -1069,14 +1139,17 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
     pl.tiles_w = (W + 7) / 8;
     pl.tiles_h = (H + 7) / 8;
     pl.pix_tiles = B * pl.tiles_w * pl.tiles_h;
+    // one CTA per SM (shared memory): size the grid to fill whole waves — the largest split count
+    // whose grid still fits in two waves (a 297-CTA grid on 148 SMs would run three)
     const int tiles = pl.groups * pl.n_tiles;
-    int splits = (2 * 148 + tiles - 1) / tiles;
+    const int slots = 2 * num_sms();
+    int splits = slots / tiles;
     if (splits > pl.pix_tiles) splits = pl.pix_tiles;
     if (splits < 1) splits = 1;
-    if (splits > 148) splits = 148;
+    if (splits > num_sms()) splits = num_sms();
     pl.splits = splits;
     pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
-    pl.bias_blocks = 296;
+    pl.bias_blocks = 148 * 6;
     pl.bias_bytes = (size_t)pl.bias_blocks * cout * sizeof(float);
     return pl;
   }
@@ -1096,7 +1169,7 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
   if (splits > 128) splits = 128;
   pl.splits = splits;
   pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
-  pl.bias_blocks = 296;
+  pl.bias_blocks = 148 * 6;
   pl.bias_bytes = (size_t)pl.bias_blocks * cout * sizeof(float);
   return pl;
 }

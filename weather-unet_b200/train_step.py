@@ -34,14 +34,15 @@ class GradBuckets:
                 cur, cur_bytes = [], 0
         if cur:
             self.buckets.append(cur)
-        self.flat, self.where = [], {}
+        self.flat, self.where, self.views, self.got = [], {}, {}, set()
         for bi, bucket in enumerate(self.buckets):
             total = sum(p.numel() for _, p in bucket)
             dev = bucket[0][1].device
             flat = torch.zeros(total, dtype=torch.float32, device=dev)
             off = 0
             for n, p in bucket:
-                p.grad = flat[off:off + p.numel()].view_as(p)
+                self.views[n] = flat[off:off + p.numel()].view_as(p)
+                p.grad = self.views[n]
                 self.where[n] = bi
                 off += p.numel()
             self.flat.append(flat)
@@ -61,21 +62,22 @@ class GradBuckets:
     def zero(self):
         for f in self.flat:
             f.zero_()
+        for bucket in self.buckets:
+            for n, p in bucket:
+                p.grad = self.views[n]
+        self.got = set()
         self.pending = [len(b) for b in self.buckets]
         self.launched = [False] * len(self.buckets)
 
     def grad_view(self, name):
-        bi = self.where[name]
-        for n, p in self.buckets[bi]:
-            if n == name:
-                return p.grad
-        raise KeyError(name)
+        return self.views[name]
 
     def ready(self, name):
         """Mark one gradient as final; launch the bucket's all-reduce when it is complete."""
         bi = self.where.get(name)
         if bi is None:
             return
+        self.got.add(name)
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
             self._launch(bi)
@@ -102,6 +104,10 @@ class GradBuckets:
             self._launch(bi)
         if self.comm_stream is not None and self.world > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for bucket in self.buckets:  # no gradient this pass -> grad None, as without data parallelism
+            for n, p in bucket:      # (the optimiser then skips it: no weight-decay-only update)
+                if n not in self.got:
+                    p.grad = None
 
 
 class GDTrainStep:
