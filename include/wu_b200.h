@@ -110,7 +110,7 @@ int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, cons
                        int C, int nc, int HW, float eps, wu_stream_t stream);
 /* Step 3 (cunet.py:59-61): u[b,Y,X,c] = keep * bilinear_x2(x*scale+shift)[b,Y,X,c] / (1-p).
  * Dropout: p_drop == 0 -> none; else if mask != NULL it is a uint8 NHWC [B][2h][2w][C] keep mask;
- * else keep bits come from a Philox4x32-10 stream keyed by (seed, element index). */
+ * else keep bits come from a Philox4x32-7 stream keyed by (seed, 8-channel vector index). */
 int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u, int B,
                          int h, int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
                          wu_stream_t stream);

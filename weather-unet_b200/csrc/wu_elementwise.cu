@@ -44,11 +44,12 @@ __device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
                : "memory");
 }
 
-// Philox4x32-10 (Salmon et al. 2011): counter = 128-bit, key = 64-bit.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+// Philox4x32 (Salmon et al. 2011), 7 rounds (the smallest round count that passes BigCrush):
+// counter = 128-bit, key = 64-bit.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
     const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -57,19 +58,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-// Keep flags for the 8 channels of vector `vec_index` (16 random bits each, keep iff u16 >= thr).
-__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t vec_index, uint32_t thr) {
-  const uint4 r = philox4x32_10(
+// Keep mask for the 8 channels of vector `vec_index`, laid out like packed bf16x2 data: 16 random
+// bits per element, lane = 0xFFFF iff u16 >= thr (one SIMD compare per element pair).
+__device__ __forceinline__ uint4 dropout_keepmask(uint64_t seed, uint64_t vec_index, uint32_t thr) {
+  const uint4 r = philox4x32(
       make_uint4((uint32_t)vec_index, (uint32_t)(vec_index >> 32), 0x77755555u, 0u),
       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  uint32_t keep = 0;
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if ((w[i] & 0xFFFFu) >= thr) keep |= 1u << (2 * i);
-    if ((w[i] >> 16) >= thr) keep |= 1u << (2 * i + 1);
-  }
-  return keep;
+  const uint32_t t2 = thr | (thr << 16);
+  return make_uint4(__vcmpgeu2(r.x, t2), __vcmpgeu2(r.y, t2), __vcmpgeu2(r.z, t2),
+                    __vcmpgeu2(r.w, t2));
 }
 __host__ __device__ inline uint32_t dropout_threshold(float p) {
   float t = p * 65536.f + 0.5f;
@@ -699,21 +696,18 @@ __device__ __forceinline__ void bilinear_src(int dst, float ratio, int in, int& 
   lam = s - (float)i0;
 }
 
-// keep flags for 8 consecutive channels: injected uint8 mask or the Philox stream
-__device__ __forceinline__ uint32_t keep_bits8(uint32_t thr, uint64_t seed,
-                                               const uint8_t* __restrict__ mask, long long vi) {
-  if (thr == 0u) return 0xFFu;
+// keep mask (packed bf16x2 lanes) for 8 consecutive channels: injected uint8 mask or Philox stream
+__device__ __forceinline__ uint4 keep_mask8(uint32_t thr, uint64_t seed,
+                                            const uint8_t* __restrict__ mask, long long vi) {
+  if (thr == 0u) return make_uint4(~0u, ~0u, ~0u, ~0u);
   if (mask != nullptr) {
     const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mask + vi * 8));
-    uint32_t keep = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if ((mv.x >> (8 * j)) & 0xFFu) keep |= 1u << j;
-      if ((mv.y >> (8 * j)) & 0xFFu) keep |= 1u << (4 + j);
-    }
-    return keep;
+    auto lanes = [](uint32_t two_bytes) -> uint32_t {
+      return ((two_bytes & 0xFFu) ? 0x0000FFFFu : 0u) | ((two_bytes & 0xFF00u) ? 0xFFFF0000u : 0u);
+    };
+    return make_uint4(lanes(mv.x), lanes(mv.x >> 16), lanes(mv.y), lanes(mv.y >> 16));
   }
-  return dropout_keep8(seed, (uint64_t)vi, thr);
+  return dropout_keepmask(seed, (uint64_t)vi, thr);
 }
 
 // grid = (ceil(2w * C/8 / 256), B * 2h): one block row per output image row, no index divisions
@@ -746,7 +740,7 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
   const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
   const long long vi = ((long long)blockIdx.y * Wo + X) * cv + v;
-  const uint32_t keep = keep_bits8(thr, seed, mask, vi);
+  const uint4 km = keep_mask8(thr, seed, mask, vi);
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx),
               w11 = ly * lx;
   float o[8];
@@ -754,10 +748,11 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   for (int j = 0; j < 8; ++j) {
     // bilinear weights sum to 1, so interpolate x first and apply the affine map once
     const float xi2 = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
-    const float z = fmaf(xi2, sc[j], sh[j]);
-    o[j] = ((keep >> j) & 1u) ? z * inv_keep : 0.f;
+    o[j] = fmaf(xi2, sc[j], sh[j]) * inv_keep;
   }
-  st_stream16(u + vi * 8, pack8(o));
+  uint4 ov = pack8(o);
+  ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
+  st_stream16(u + vi * 8, ov);
 }
 
 // Weight with which destination index D contributes to source index s (0 if it does not).
@@ -792,13 +787,14 @@ adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __r
     const float wx = bilinear_adjoint_w(X, xx, rw, w, Wo);
     if (wx != 0.f) {
       const long long vi = (row + X) * cv + v;
+      uint4 gv = ld_stream16(gu + vi * 8);
+      const uint4 km = keep_mask8(thr, seed, mask, vi);
+      gv.x &= km.x; gv.y &= km.y; gv.z &= km.z; gv.w &= km.w;
       float f[8];
-      unpack8(ld_stream16(gu + vi * 8), f);
-      const uint32_t keep = keep_bits8(thr, seed, mask, vi);
+      unpack8(gv, f);
       const float wgt = wx * inv_keep;
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if ((keep >> e) & 1u) acc[e] = fmaf(wgt, f[e], acc[e]);
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, f[e], acc[e]);
     }
   }
   *reinterpret_cast<uint4*>(t + (((long long)blockIdx.y * w + xx) * cv + v) * 8) = pack8(acc);

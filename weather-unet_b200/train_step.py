@@ -41,7 +41,8 @@ class GradBuckets:
             flat = torch.zeros(total, dtype=torch.float32, device=dev)
             off = 0
             for n, p in bucket:
-                self.views[n] = flat[off:off + p.numel()].view_as(p)
+                # same strides as the parameter (contiguous or channels_last): autograd's layout contract
+                self.views[n] = torch.as_strided(flat, p.shape, p.stride(), storage_offset=off)
                 p.grad = self.views[n]
                 self.where[n] = bi
                 off += p.numel()
@@ -119,14 +120,16 @@ class GDTrainStep:
     """
 
     def __init__(self, G, D, lr=1e-4, estimator=None, d_autocast=True, eps_con=1e-2, group=None,
-                 overlap=True):
+                 overlap=True, distributed=None):
         self.G, self.D, self.estimator = G, D, estimator
         self.d_autocast = d_autocast
         self.d_channels_last = next(D.parameters()).is_cuda
         if self.d_channels_last:  # cuDNN's bf16 tensor-core kernels are NHWC: avoid per-conv transposes
             D.to(memory_format=torch.channels_last)
         self.eps_con = eps_con  # 1e-2 supervised, 1e-7 otherwise (t_cls_train.py:259-266)
-        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.distributed = bool(distributed)
         self.g_buckets = self.d_buckets = None
         if self.distributed:
             skip = tuple(n for n, _ in G.named_parameters() if n.endswith("emb.weight"))
