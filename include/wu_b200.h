@@ -114,6 +114,10 @@ int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, cons
 int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u, int B,
                          int h, int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
                          wu_stream_t stream);
+/* AdaIN without the fused upsample / dropout (utils.py:49-50 on its own): out = x*scale + shift,
+ * scale / shift from wu_adain_style_fwd.  x, out NHWC bf16 [B][HW][C]. */
+int wu_adain_apply(const void* x, const float* scale, const float* shift, void* out, int B, int HW,
+                   int C, wu_stream_t stream);
 /* Backward, step 1: gz = adjoint(dropout o upsample)(gu) at low resolution, plus per-(b,c)
  * partial sums S1 = sum gz, S2 = sum gz * xhat (xhat = (x-mean)*rstd).  Separable: a horizontal
  * pass (applies the dropout mask) into `scratch` (bf16 [B][2h][w][C],
@@ -133,6 +137,16 @@ int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb, cons
 int wu_adain_bwd_apply(const void* gz, const void* x, const float* mean, const float* rstd,
                        const float* ystd, const float* k1, const float* k2, void* gx, int B,
                        int HW, int C, wu_stream_t stream);
+
+/* ---- bias + LeakyReLU on NHWC bf16 (discriminator blocks, nets.py:26-33) ---------
+ * fwd, in place: x = leaky_relu(x + bias[c], slope); slope == 1 is a plain bias add.
+ * bwd: g = gy * (y > 0 ? 1 : slope) (g may alias gy), db[c] = sum_px g[px][c] (fp32, overwritten).
+ * x, y, gy, g: bf16 [npix][C]; C a power of two in [8, 2048]. */
+int wu_bias_act_fwd(void* x, const float* bias, float slope, long long npix, int C,
+                    wu_stream_t stream);
+size_t wu_bias_act_bwd_workspace_bytes(int C);
+int wu_bias_act_bwd(const void* gy, const void* y, void* g, float* db, float slope, long long npix,
+                    int C, void* workspace, size_t workspace_bytes, wu_stream_t stream);
 
 /* ---- layout helpers (tests, interop with NCHW fp32 PyTorch tensors) ---------------------------*/
 int wu_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W,

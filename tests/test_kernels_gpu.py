@@ -235,3 +235,31 @@ def test_errors(cuda):
         K.conv3x3(x, None, w, None, True, None, 64)
     with pytest.raises(WuError):
         K.maxpool2(torch.zeros(1, 7, 8, 64, dtype=torch.bfloat16, device=cuda))
+
+
+def test_standalone_blocks(cuda):
+    """r_double_conv and AdaIN used on their own (forward only) match the oracle's functions."""
+    from oracle import cunet_oracle as orc
+    from weather_unet_b200.nets import r_double_conv
+    from weather_unet_b200.utils import AdaIN
+    torch.manual_seed(4)
+    blk = r_double_conv(64, 128).to(cuda)
+    x = bf(torch.randn(2, 64, 16, 24)).to(cuda)
+    sd = {f"b.{k}": v for k, v in blk.state_dict().items()}
+    with torch.no_grad():
+        y = blk(x)
+        ref = orc.double_conv(sd, "b", x)
+    assert y.shape == ref.shape and rel(y, ref) < 8e-3
+    first = r_double_conv(3, 64).to(cuda)
+    xi = torch.rand(2, 3, 16, 24, device=cuda) * 2 - 1
+    with torch.no_grad():
+        assert rel(first(xi), orc.double_conv({f"b.{k}": v for k, v in first.state_dict().items()}, "b", xi)) < 8e-3
+    ad = AdaIN(128, num_classes=5).to(cuda)
+    xa = bf(torch.randn(2, 128, 8, 8)).to(cuda)
+    c = torch.randn(2, 5, device=cuda)
+    with torch.no_grad():
+        ya = ad(xa, c)
+        ra = orc.adain({f"a.{k}": v for k, v in ad.state_dict().items()}, "a", xa, c)
+    assert rel(ya, ra) < 6e-3
+    with pytest.raises(RuntimeError, match="forward-only"):
+        blk(x.requires_grad_(True))

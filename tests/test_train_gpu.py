@@ -1,0 +1,99 @@
+"""Training-step parity on the GPU: the fused bias+LeakyReLU kernels, the discriminator fast path,
+and a fixed-seed loss curve of GDTrainStep against the curve recorded from the reference modules
+(tests/golden/train_b2_h32_seed0.npz), with the same dropout masks injected."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "train_b2_h32_seed0.npz")
+
+
+@pytest.mark.parametrize("B,C,H,W,slope", [(2, 64, 16, 16, 0.2), (3, 128, 8, 24, 1.0), (1, 512, 4, 4, 0.2)])
+def test_bias_act(cuda, B, C, H, W, slope):
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(B, C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(C, generator=g).to(cuda)
+    gy = torch.randn(B, C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    xr = x.float().clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.leaky_relu(xr + br.view(1, -1, 1, 1), slope)
+    ref.backward(gy.float())
+    xin = x.clone().requires_grad_(True)
+    bin_ = b.clone().requires_grad_(True)
+    y = K.bias_act(xin * 1.0, bin_, slope)  # xin * 1.0: a non-leaf the op may overwrite
+    assert ((y.float() - ref).norm() / ref.norm()).item() < 4e-3
+    y.backward(gy)
+    assert ((xin.grad.float() - xr.grad).norm() / xr.grad.norm()).item() < 4e-3
+    assert ((bin_.grad - br.grad).norm() / br.grad.norm()).item() < 2e-3
+
+
+def test_disc_fast_path(cuda):
+    """SNDisc under bf16 autocast + channels_last takes the fused kernels; outputs and gradients
+    agree with the plain PyTorch module path in the same precision."""
+    from weather_unet_b200.disc import SNDisc
+    from weather_unet_b200 import _ops as K
+    torch.manual_seed(100)
+    d1 = SNDisc(5).to(cuda).train().to(memory_format=torch.channels_last)
+    torch.manual_seed(100)
+    d2 = SNDisc(5).to(cuda).train().to(memory_format=torch.channels_last)
+    x = (torch.rand(4, 3, 64, 64, device=cuda) * 2 - 1).contiguous(memory_format=torch.channels_last)
+    c = torch.eye(5, device=cuda)[:4]
+    n0 = K.launch_count()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o1 = d1(x, c)[0].float()
+    assert K.launch_count() > n0, "fast path not taken"
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        h = x
+        for i in range(1, 5):
+            h = getattr(d2, f"conv{i}")(h)  # plain nn.Sequential path
+        pooled = h.sum(dim=(2, 3))
+        o2 = (d2.l(pooled) + (d2.embed(c) * pooled).sum(1, keepdim=True)).float()
+    assert torch.allclose(o1, o2, rtol=3e-2, atol=3e-2 * o2.abs().max().item())
+    o1.sum().backward()
+    o2.sum().backward()
+    for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
+        r = ((p.grad.float() - q.grad.float()).norm() / (q.grad.float().norm() + 1e-12)).item()
+        assert r < 5e-2, f"{n}: {r}"
+
+
+def test_loss_curve_against_reference_golden(cuda):
+    from weather_unet_b200 import Conditional_UNet
+    from weather_unet_b200.disc import SNDisc
+    from weather_unet_b200.train_step import GDTrainStep
+    z = np.load(GOLD)
+    torch.manual_seed(0)
+    G = Conditional_UNet(5).to(cuda).train()
+    torch.manual_seed(100)
+    D = SNDisc(5).to(cuda).train()
+    step = GDTrainStep(G, D, lr=float(z["lr"][0]), d_autocast=False)   # fp32 D isolates the generator
+    x, cr, ct = (torch.from_numpy(z[k]).to(cuda) for k in ("images", "c_real", "c_target"))
+    keys = [str(k) for k in z["keys"]]
+    B, H = x.shape[0], x.shape[2]
+    shapes = [(B, H // 4, H // 4, 512), (B, H // 2, H // 2, 256), (B, H, H, 128)]
+
+    def masks(i):
+        out = []
+        for j, s in enumerate(shapes):
+            bits = np.unpackbits(z[f"mask_{i}_{j}"])[:int(np.prod(s))]
+            out.append(torch.from_numpy(bits.reshape(s).astype(np.uint8)).to(cuda))
+        return tuple(out)
+
+    curve = []
+    for it in range(z["curve"].shape[0]):
+        out = step.step(x, cr, ct, masks_d=masks(2 * it), masks_g=masks(2 * it + 1))
+        curve.append([float(out[k]) for k in keys])
+    curve = np.array(curve)
+    print(np.array2string(curve, precision=4), "\n", np.array2string(z["curve"], precision=4))
+    # fixed seed, injected masks: per-step |dloss| / max(|loss|, 1) <= 5e-2 on the
+    # large terms; g_loss_adv / d_loss sit near zero and chaotic GAN dynamics at lr 1e-3 amplify
+    # bf16 differences after a few iterations, so they are held to the first 3 iterations
+    big = [keys.index(k) for k in ("g_loss", "loss_con", "g_loss_l1")]
+    ref = z["curve"]
+    err = np.abs(curve - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err[:, big].max() < 5e-2, err
+    assert err[:3].max() < 1.5e-1, err

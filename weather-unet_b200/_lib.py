@@ -6,7 +6,7 @@ the first call raises.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint64, c_ulonglong, c_void_p
 
 import torch
 
@@ -36,11 +36,15 @@ SIGNATURES = {
     "wu_adain_stats_chunks": (I, [I]),
     "wu_adain_stats": (I, [P, P, I, I, I, P]),
     "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, P]),
+    "wu_adain_apply": (I, [P, P, P, P, I, I, I, P]),
     "wu_adain_up_drop_fwd": (I, [P, P, P, P, I, I, I, I, F, U64, P, P]),
     "wu_adain_up_drop_bwd_scratch_bytes": (SZ, [I, I, I, I]),
     "wu_adain_up_drop_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, U64, P, P]),
     "wu_adain_style_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
     "wu_adain_bwd_apply": (I, [P, P, P, P, P, P, P, P, I, I, I, P]),
+    "wu_bias_act_fwd": (I, [P, P, F, c_longlong, I, P]),
+    "wu_bias_act_bwd_workspace_bytes": (SZ, [I]),
+    "wu_bias_act_bwd": (I, [P, P, P, P, F, c_longlong, I, P, SZ, P]),
     "wu_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
     "wu_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),
 }

@@ -127,6 +127,22 @@ def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask):
     return u, st
 
 
+def adain_apply(x, cond, lw, lb, eps):
+    """AdaIN(x, cond) on its own (utils.py:41-51): x (B,h,w,C) NHWC bf16 -> same shape."""
+    B, h, w, C = x.shape
+    nc = cond.shape[1]
+    dev = x.device
+    nchunk = query("wu_adain_stats_chunks", h * w)
+    partial = torch.empty((B, nchunk, C, 2), dtype=torch.float32, device=dev)
+    call("wu_adain_stats", ptr(x), ptr(partial), B, h * w, C, stream())
+    buf = torch.empty((5, B, C), dtype=torch.float32, device=dev)
+    call("wu_adain_style_fwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(buf[0]), ptr(buf[1]),
+         ptr(buf[2]), ptr(buf[3]), ptr(buf[4]), B, C, nc, h * w, float(eps), stream())
+    out = torch.empty_like(x)
+    call("wu_adain_apply", ptr(x), ptr(buf[3]), ptr(buf[4]), ptr(out), B, h * w, C, stream())
+    return out
+
+
 def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
     """-> (gx masked by relu'(x), dlw [4C][nc], dlb [4C])."""
     B, h, w, C = x.shape
@@ -148,6 +164,46 @@ def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
     call("wu_adain_bwd_apply", ptr(gz), ptr(x), ptr(st.mean), ptr(st.rstd), ptr(st.ystd), ptr(kk[0]),
          ptr(kk[1]), ptr(gx), B, h * w, C, stream())
     return gx, dlw, dlb
+
+
+class _BiasAct(torch.autograd.Function):
+    """y = leaky_relu(x + bias, slope) in place on a channels_last bf16 (B, C, H, W) tensor (== NHWC
+    memory), with a one-pass backward (masked gradient + deterministic bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, slope):
+        B, C, H, W = x.shape
+        call("wu_bias_act_fwd", ptr(x), ptr(bias), float(slope), B * H * W, C, stream())
+        ctx.mark_dirty(x)
+        ctx.save_for_backward(x)
+        ctx.slope = float(slope)
+        return x
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        B, C, H, W = y.shape
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        if gy.dtype != BF16:
+            gy = gy.to(BF16)
+        g = torch.empty_like(gy)
+        db = torch.empty((C,), dtype=torch.float32, device=y.device)
+        nbytes = query("wu_bias_act_bwd_workspace_bytes", C)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=y.device)
+        call("wu_bias_act_bwd", ptr(gy), ptr(y), ptr(g), ptr(db), ctx.slope, B * H * W, C, ptr(ws),
+             nbytes, stream())
+        return g, (db if ctx.needs_input_grad[1] else None), None
+
+
+def bias_act_supported(x):
+    """channels_last bf16 CUDA tensor with a power-of-two channel count >= 8."""
+    C = x.shape[1]
+    return (x.is_cuda and x.dtype == BF16 and x.dim() == 4 and C >= 8 and (C & (C - 1)) == 0
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def bias_act(x, bias, slope):
+    return _BiasAct.apply(x, bias.float() if bias.dtype != torch.float32 else bias, slope)
 
 
 def nchw_to_nhwc(x):

@@ -814,7 +814,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
 // ------------------------------------------------------------------------------------------------
 // v1 gives every CTA two (tap, channel block) atoms, so the dY tile is re-fetched for each pair
 // and every X tile once per tap (ncu: L2 -> SMEM bound, tensor pipe ~22 %).  v2 gives a CTA up to
-// NC "copies" = (column shift s, channel block cb) pairs; one TMA box (64 ch, 8 px, 8+2 rows) per
+// NC "copies" = (channel block cb, column shift s) pairs; one TMA box (64 ch, 8 px, 8+2 rows) per
 // copy and pixel tile serves the three taps r = 0..2 of that column shift through start-address
 // offsets of r KiB (8 pixels x 128 B: 1024-byte aligned), and one dY tile feeds all 3*NC atoms:
 //   M-blocks (128 accumulator lanes = two 64-row atoms) per CTA:
@@ -872,12 +872,14 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // blockIdx.x -> (copy group, n tile, split)
+  // blockIdx.x -> (split, copy group, n tile) with the split slowest: the CTAs that walk the same
+  // pixel range (all copy groups / n tiles of one split) are neighbours in launch order, run at
+  // the same time and share their X / dY tiles through L2 instead of re-reading them from HBM
   int id = blockIdx.x;
-  const int z = id % p.splits;
-  id /= p.splits;
   const int nt = id % p.n_tiles;
-  const int grp = id / p.n_tiles;
+  id /= p.n_tiles;
+  const int grp = id % p.groups;
+  const int z = id / p.groups;
   const int n0 = nt * BN;
   const int g0 = grp * NC;                                       // first global copy id
   const int nc = (p.copies - g0) < NC ? (p.copies - g0) : NC;    // copies of this CTA
@@ -921,8 +923,8 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
         const uint32_t a_dst = base + stage * Cfg::kStageBytes;
         const uint32_t b_dst = a_dst + Cfg::kABytes;
         for (int c = 0; c < nc; ++c) {
-          const int g = g0 + c;
-          const int s = g / p.ctot_blocks, cb = g - s * p.ctot_blocks;
+          const int g = g0 + c;  // global copy id = cb * 3 + s: the three column shifts of a
+          const int cb = g / 3, s = g - cb * 3;  // channel block are fetched together (L2 hits)
           if (cb < p.c0_blocks)
             tma_load_4d(a_dst + c * Cfg::kCopyBytes, &tmX0, fb, cb * 64, w0 + s - 1, h0 - 1, b);
           else
@@ -994,7 +996,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
       }
       const bool valid = c < nc;
       const int g = g0 + (valid ? c : 0);
-      const int s = g / p.ctot_blocks, cb = g - s * p.ctot_blocks;
+      const int cb = g / 3, s = g - cb * 3;
       const int tap = r * 3 + s;
       float* out = p.partial +
                    ((size_t)z * 9 * p.cin_total + (size_t)tap * p.cin_total + cb * 64 + r64) * p.cout + n0;

@@ -901,6 +901,26 @@ __global__ void adain_style_bwd_params_kernel(const float* __restrict__ gh,
   }
 }
 
+// AdaIN on its own (no upsample / dropout): out = x * scale[b,c] + shift[b,c]
+__global__ void __launch_bounds__(256)
+adain_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int B, int HW,
+                   int C) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * HW * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    const int b = (int)(i / ((long long)HW * cv));
+    const long long pc = (long long)b * C + v * 8;
+    float f[8];
+    unpack8(ld_stream16(x + i * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], __ldg(scale + pc + j), __ldg(shift + pc + j));
+    st_stream16(out + i * 8, pack8(f));
+  }
+}
+
 // gx = (x > 0) * rstd * ystd * (gz - k1 - xhat * k2)
 __global__ void __launch_bounds__(256)
 adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ gz, const __nv_bfloat16* __restrict__ x,
@@ -1148,6 +1168,16 @@ extern "C" int wu_adain_style_bwd(const float* cond, const float* lw, const floa
   WU_CHECK_LAUNCH("adain_style_bwd_kernel");
   adain_style_bwd_params_kernel<<<(4 * C + 127) / 128, 128, 0, st>>>(gh, cond, dlw, dlb, B, 4 * C, nc);
   WU_CHECK_LAUNCH("adain_style_bwd_params_kernel");
+  return WU_OK;
+}
+extern "C" int wu_adain_apply(const void* x, const float* scale, const float* shift, void* out,
+                              int B, int HW, int C, wu_stream_t stream) {
+  WU_REQUIRE(x && scale && shift && out && B > 0 && HW > 0, "wu_adain_apply: bad args");
+  WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_apply: C=%d must be a multiple of 8", C);
+  const long long total = (long long)B * HW * (C / 8);
+  adain_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, scale, shift, (bf16*)out, B, HW, C);
+  WU_CHECK_LAUNCH("adain_apply_kernel");
   return WU_OK;
 }
 extern "C" int wu_adain_bwd_apply(const void* gz, const void* x, const float* mean,

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+
 namespace wu {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

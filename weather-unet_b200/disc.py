@@ -6,6 +6,7 @@ list [out, c1, c2, c3, c4]."""
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 try:
     from .nets import sn_double_conv
@@ -29,11 +30,30 @@ class SNDisc(nn.Module):
         self.embed = nn.utils.spectral_norm(nn.Linear(num_classes, 512, bias=True))
         nn.init.xavier_uniform_(self.embed.weight)
 
+    @staticmethod
+    def _sn_conv(conv, h, slope):
+        """Spectral-norm convolution + bias (+ LeakyReLU when slope != 1).  On a bf16
+        channels_last CUDA activation the bias add and the activation run in one sm_100a kernel
+        (wu_bias_act_*) instead of separate ATen passes; anywhere else this is the plain module."""
+        for hook in conv._forward_pre_hooks.values():  # spectral_norm: power iteration, W / sigma
+            hook(conv, (h,))
+        out = F.conv2d(h, conv.weight, None, conv.stride, conv.padding)
+        try:
+            from . import _ops as K
+        except ImportError:
+            from weather_unet_b200 import _ops as K
+        if K.bias_act_supported(out):
+            return K.bias_act(out, conv.bias, slope)
+        out = out + conv.bias.to(out.dtype).view(1, -1, 1, 1)
+        return out if slope == 1.0 else F.leaky_relu(out, slope)
+
     def forward(self, x, c=None):
         feats = []
         h = x
         for i in range(1, 5):
-            h = getattr(self, f"conv{i}")(h)
+            blk = getattr(self, f"conv{i}")
+            h = self._sn_conv(blk[0], h, 1.0)                       # no activation in between
+            h = self._sn_conv(blk[1], h, blk[2].negative_slope)     # (nets.py:26-33)
             feats.append(h)
         pooled = feats[-1].sum(dim=(2, 3))  # global SUM pool (disc.py:32)
         out = self.l(pooled)
