@@ -473,6 +473,10 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer (one thread)
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      // descriptors are built once; per MMA only (byte offset >> 4) is added to the start-address
+      // field (the single issuing thread's instruction count paces the tensor pipe at small N)
+      const uint64_t adesc0 = umma_smem_desc_sw128(a_base, 16, 1024);
+      const uint64_t bdesc0 = umma_smem_desc_sw128(b_base, 16, 1024);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -485,19 +489,19 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
           for (int s = 0; s < 3; ++s) {
             mbar_wait(fullA(sa), pa);
             tc_fence_after();
-            const uint32_t a_addr = a_base + sa * Cfg::kABytes;
+            const uint64_t adesc_s = adesc0 + (uint64_t)((sa * Cfg::kABytes) >> 4);
             for (int r = 0; r < 3; ++r) {
               mbar_wait(fullB(sb), pb);
               tc_fence_after();
-              const uint32_t b_addr = b_base + sb * Cfg::kBBytes;
+              const uint64_t bdesc_s = bdesc0 + (uint64_t)((sb * Cfg::kBBytes) >> 4);
+              const uint64_t adesc_r = adesc_s + (uint64_t)((r * 1024) >> 4);
               const uint32_t first = (cb | s | r) == 0 ? 1u : 0u;
 #pragma unroll
               for (int t = 0; t < T; ++t) {
-                const uint32_t at = a_addr + (16 * t + r) * 1024;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t adesc = umma_smem_desc_sw128(at + k * 32, 16, 1024);
-                  const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                  const uint64_t adesc = adesc_r + (uint64_t)((16 * t * 1024 + k * 32) >> 4);
+                  const uint64_t bdesc = bdesc_s + (uint64_t)((k * 32) >> 4);
                   umma_bf16(d_tmem + t * BN, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
                 }
               }
@@ -944,28 +948,46 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
       const int npair = (nc + 1) >> 1;
+      const int nblocks = nc + npair;
+      // One thread issues every MMA, so its instruction count per MMA is what paces the tensor
+      // pipe at small N: build each accumulator block's A descriptor ONCE (stage 0, k = 0) and
+      // only add (byte offset >> 4) to the start-address field per stage / k step.
+      uint64_t adesc0[Cfg::kBlocks];
+#pragma unroll
+      for (int blk = 0; blk < Cfg::kBlocks; ++blk) {
+        uint32_t addr, lbo;
+        if (blk < NC) {  // [r=0 | r=1] of copy blk
+          addr = base + blk * Cfg::kCopyBytes;
+          lbo = 1024u;
+        } else {         // [r=2 of copy 2j | r=2 of copy 2j+1]
+          const int j = blk - NC;
+          addr = base + 2 * j * Cfg::kCopyBytes + 2 * 1024;
+          lbo = (2 * j + 1 < nc) ? (uint32_t)Cfg::kCopyBytes : 1024u;
+        }
+        adesc0[blk] = umma_smem_desc_sw128(addr, lbo, 1024);
+      }
+      const uint64_t bdesc0 = umma_smem_desc_sw128(base + Cfg::kABytes, Cfg::kAtomBytes, 1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = pt_begin; pt < pt_end; ++pt) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t a_addr = base + stage * Cfg::kStageBytes;
-        const uint32_t b_addr = a_addr + Cfg::kABytes;
+        const uint64_t soff = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
         const uint32_t acc = pt != pt_begin ? 1u : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 pixels = 2 rows of 8 = 2 KiB)
-          const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, Cfg::kAtomBytes, 1024);
-          for (int c = 0; c < nc; ++c) {  // [r=0 | r=1] of copy c
-            const uint64_t adesc =
-                umma_smem_desc_sw128(a_addr + c * Cfg::kCopyBytes + k * 2048, 1024, 1024);
-            umma_bf16(tmem_base + c * BN, adesc, bdesc, idesc, (acc | (uint32_t)k) != 0 ? 1u : 0u);
-          }
-          for (int j = 0; j < npair; ++j) {  // [r=2 of copy 2j | r=2 of copy 2j+1]
-            const uint32_t lbo = (2 * j + 1 < nc) ? (uint32_t)Cfg::kCopyBytes : 1024u;
-            const uint64_t adesc = umma_smem_desc_sw128(
-                a_addr + 2 * j * Cfg::kCopyBytes + 2 * 1024 + k * 2048, lbo, 1024);
-            umma_bf16(tmem_base + (nc + j) * BN, adesc, bdesc, idesc,
-                      (acc | (uint32_t)k) != 0 ? 1u : 0u);
+          const uint64_t koff = soff + (uint64_t)((k * 2048) >> 4);
+          const uint64_t bdesc = bdesc0 + koff;
+          const uint32_t accum = (acc | (uint32_t)k) != 0 ? 1u : 0u;
+#pragma unroll
+          for (int blk = 0; blk < Cfg::kBlocks; ++blk) {
+            // TMEM column of block blk: copies first (blk < nc), then the r=2 pairs
+            const bool is_copy = blk < NC;
+            const bool live = is_copy ? (blk < nc) : (blk - NC < npair);
+            if (live) {
+              const int col = is_copy ? blk : nc + (blk - NC);
+              umma_bf16(tmem_base + col * BN, adesc0[blk] + koff, bdesc, idesc, accum);
+            }
           }
         }
         umma_commit(empty_bar(stage));
@@ -974,6 +996,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
           phase ^= 1u;
         }
       }
+      (void)nblocks;
       umma_commit(tfull_bar);
     }
   } else {
