@@ -37,7 +37,28 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / transfer legs")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
+
+
+def g_conv_flops(H, W):
+    """2*MAC of the generator's 15 convolutions, one image, forward (84.81 GF @256)."""
+    plan = [(3, 64, 1), (64, 64, 1), (64, 128, 2), (128, 128, 2), (128, 256, 4), (256, 256, 4),
+            (256, 512, 8), (512, 512, 8), (768, 256, 4), (256, 256, 4), (384, 128, 2), (128, 128, 2),
+            (192, 64, 1), (64, 64, 1)]
+    total = sum(2 * 9 * ci * co * (H // d) * (W // d) for ci, co, d in plan)
+    return total + 2 * 64 * 3 * H * W
+
+
+def d_conv_flops(H, W):
+    """2*MAC of the discriminator's 8 convolutions, one image, forward (5.50 GF @256)."""
+    total, h, w = 0, H, W
+    for cin, cout in ((3, 64), (64, 128), (128, 256), (256, 512)):
+        total += 2 * 9 * cin * cin * h * w
+        h, w = h // 2, w // 2
+        total += 2 * 9 * cin * cout * h * w
+    return total
 
 
 def peaks():
@@ -158,8 +179,6 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import cunet_oracle as orc_flops  # FLOP bookkeeping only (no compute)
-    from oracle import train_oracle as step_flops
     from weather_unet_b200 import Conditional_UNet, _ops as K
     from weather_unet_b200.disc import SNDisc
     from weather_unet_b200.train_step import GDTrainStep
@@ -212,11 +231,15 @@ def run_ours(args):
         sampler.start()
     n0 = K.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         losses = trainer.step(*resident[i % n_host])
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = K.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
@@ -333,11 +356,12 @@ def run_ours(args):
                               f"reference train step, fp32 torch CPU, batch {args.ref_batch}, {S}x{S}"}
 
     if rank == 0:
-        flops_step = step_flops.step_flops(S, S, B)            # reference-faithful count
-        executed = B * (orc_flops.conv_flops(S, S) * 2          # 2 G forward
-                        + 2 * orc_flops.conv_flops(S, S) - 2 * 9 * 3 * 64 * S * S   # 1 G backward
-                        + 3 * step_flops.disc_conv_flops(S, S)  # 3 D forward
-                        + 5 * step_flops.disc_conv_flops(S, S))  # 2 D full backward + 1 dgrad-only
+        gf, df = g_conv_flops(S, S), d_conv_flops(S, S)
+        g_bwd = 2 * gf - 2 * 9 * 3 * 64 * S * S                 # no data gradient for the image
+        flops_step = B * (2 * gf + g_bwd + 3 * df + 6 * df)     # reference-faithful count (388.8 GF/img)
+        executed = B * (2 * gf + g_bwd                          # 2 G forward + 1 G backward
+                        + 3 * df                                # 3 D forward
+                        + 5 * df)                               # 2 D full backward + 1 dgrad-only
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,

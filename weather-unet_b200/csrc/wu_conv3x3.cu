@@ -129,15 +129,12 @@ __device__ __forceinline__ void epilogue_half_r(uint32_t (&v)[32], const float* 
   if (use_mask) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t mm[4] = {mreg[j].x, mreg[j].y, mreg[j].z, mreg[j].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t lo = mm[e] & 0xFFFFu, hi = mm[e] >> 16;
-        uint32_t keep = 0;
-        if (lo != 0 && (lo & 0x8000u) == 0) keep |= 0x0000FFFFu;  // bf16 value > 0
-        if (hi != 0 && (hi & 0x8000u) == 0) keep |= 0xFFFF0000u;
-        pk[4 * j + e] &= keep;
-      }
+      // bf16 value > 0  <=>  its bit pattern > 0 as a signed 16-bit integer: one SIMD compare
+      // per element pair (keeps the epilogue warps' issue slots free for the MMA thread)
+      pk[4 * j + 0] &= __vcmpgts2(mreg[j].x, 0u);
+      pk[4 * j + 1] &= __vcmpgts2(mreg[j].y, 0u);
+      pk[4 * j + 2] &= __vcmpgts2(mreg[j].z, 0u);
+      pk[4 * j + 3] &= __vcmpgts2(mreg[j].w, 0u);
     }
   }
 }
@@ -826,6 +823,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
 //     [r=2 of copy c | r=2 of c+1]   atoms one copy apart -> LBO = 10 KiB   (one per copy pair)
 //   TMEM columns = (NC + ceil(NC/2)) * BN  (NC = 5, BN = 64: 512;  NC = 2, BN = 128: 384).
 // A lone r=2 atom is issued as an M=128 block whose upper half is never read back.
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 struct WgradParams2 {
   int c0_blocks, ctot_blocks;
   int copies;  // 3 * ctot_blocks
@@ -969,7 +969,9 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
       const uint64_t bdesc0 = umma_smem_desc_sw128(base + Cfg::kABytes, Cfg::kAtomBytes, 1024);
       int stage = 0;
       uint32_t phase = 0;
-      for (int pt = pt_begin; pt < pt_end; ++pt) {
+      // FULL: every copy slot of the CTA is in use (nc == NC) -> no per-MMA liveness tests
+      auto issue_stage = [&](auto full_tag, int pt) {
+        constexpr bool FULL = decltype(full_tag)::value;
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint64_t soff = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
@@ -983,10 +985,14 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
           for (int blk = 0; blk < Cfg::kBlocks; ++blk) {
             // TMEM column of block blk: copies first (blk < nc), then the r=2 pairs
             const bool is_copy = blk < NC;
-            const bool live = is_copy ? (blk < nc) : (blk - NC < npair);
-            if (live) {
-              const int col = is_copy ? blk : nc + (blk - NC);
-              umma_bf16(tmem_base + col * BN, adesc0[blk] + koff, bdesc, idesc, accum);
+            if (FULL) {
+              umma_bf16(tmem_base + blk * BN, adesc0[blk] + koff, bdesc, idesc, accum);
+            } else {
+              const bool live = is_copy ? (blk < nc) : (blk - NC < npair);
+              if (live) {
+                const int col = is_copy ? blk : nc + (blk - NC);
+                umma_bf16(tmem_base + col * BN, adesc0[blk] + koff, bdesc, idesc, accum);
+              }
             }
           }
         }
@@ -995,6 +1001,11 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
           stage = 0;
           phase ^= 1u;
         }
+      };
+      if (nc == NC) {
+        for (int pt = pt_begin; pt < pt_end; ++pt) issue_stage(TrueTag{}, pt);
+      } else {
+        for (int pt = pt_begin; pt < pt_end; ++pt) issue_stage(FalseTag{}, pt);
       }
       (void)nblocks;
       umma_commit(tfull_bar);
@@ -1153,7 +1164,7 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
   pl.v2 = conv_impl() != 1;
   if (pl.v2) {
     pl.bn = cout >= 128 ? 128 : 64;
-    pl.nc = pl.bn == 64 ? 5 : 2;
+    pl.nc = pl.bn == 64 ? (cin_total == 64 ? 3 : 5) : 2;
     pl.n_tiles = cout / pl.bn;
     const int copies = 3 * (cin_total / 64);
     pl.groups = (copies + pl.nc - 1) / pl.nc;
@@ -1394,7 +1405,8 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     if ((rc = make_act_tmap(&ym, dy, B, H, W, cout, cout, 8, 8)) != WU_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = pl.groups * pl.n_tiles * pl.splits;
-    if (pl.bn == 64) rc = launch_wgrad2<64, 5>(x0, x1, ym, q, grid, st);
+    if (pl.bn == 64 && pl.nc == 3) rc = launch_wgrad2<64, 3>(x0, x1, ym, q, grid, st);
+    else if (pl.bn == 64) rc = launch_wgrad2<64, 5>(x0, x1, ym, q, grid, st);
     else rc = launch_wgrad2<128, 2>(x0, x1, ym, q, grid, st);
     if (rc != WU_OK) return rc;
     return wgrad_finish(q.partial, dw, db, dy, workspace, pl, cin, cout, B, H, W, st);
