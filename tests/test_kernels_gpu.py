@@ -170,7 +170,8 @@ def _adain_ref(x, c, lw, lb, eps, mask, p):
 
 
 @pytest.mark.parametrize("B,h,w,C,nc,p", [(2, 8, 8, 512, 5, 0.3), (3, 16, 24, 128, 5, 0.3),
-                                          (1, 32, 32, 256, 6, 0.0), (2, 4, 4, 128, 5, 0.3)])
+                                          (1, 32, 32, 256, 6, 0.0), (2, 4, 4, 128, 5, 0.3),
+                                          (2, 5, 7, 128, 5, 0.3)])
 def test_adain_up_drop(cuda, B, h, w, C, nc, p):
     from weather_unet_b200 import _ops as K
     g = torch.Generator(device="cpu").manual_seed(C + h)

@@ -1128,13 +1128,24 @@ bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict
     partial[(size_t)blockIdx.x * C + c] = s;
   }
 }
-__global__ void bias_grad_final_kernel(const float* __restrict__ partial, float* __restrict__ db,
-                                       int nblocks, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// db[c] = sum_b partial[b][c]: one block per 32 channels, 8 threads share a channel's block range
+__global__ void __launch_bounds__(256)
+bias_grad_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int nblocks,
+                       int C) {
+  __shared__ float red[8][32];
+  const int cl = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * C + c];
-  db[c] = s;
+  if (c < C)
+    for (int b = part; b < nblocks; b += 8) s += partial[(size_t)b * C + c];
+  red[part][cl] = s;
+  __syncthreads();
+  if (part == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cl];
+    db[c] = t;
+  }
 }
 
 template <int BN>
@@ -1185,7 +1196,7 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
     if (splits > num_sms()) splits = num_sms();
     pl.splits = splits;
     pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
-    pl.bias_blocks = 148 * 6;
+    pl.bias_blocks = 148 * 4;
     pl.bias_bytes = (size_t)pl.bias_blocks * cout * sizeof(float);
     return pl;
   }
@@ -1205,7 +1216,7 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
   if (splits > 128) splits = 128;
   pl.splits = splits;
   pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
-  pl.bias_blocks = 148 * 6;
+  pl.bias_blocks = 148 * 4;
   pl.bias_bytes = (size_t)pl.bias_blocks * cout * sizeof(float);
   return pl;
 }
@@ -1351,7 +1362,7 @@ static int wgrad_finish(const float* partial, float* dw, float* db, const void* 
     bias_grad_partial_kernel<<<pl.bias_blocks, 256, groups * cout * sizeof(float), st>>>(
         (const __nv_bfloat16*)dy, bpart, npix, cout);
     WU_CHECK_LAUNCH("bias_grad_partial_kernel");
-    bias_grad_final_kernel<<<(cout + 127) / 128, 128, 0, st>>>(bpart, db, pl.bias_blocks, cout);
+    bias_grad_final_kernel<<<(cout + 31) / 32, 256, 0, st>>>(bpart, db, pl.bias_blocks, cout);
     WU_CHECK_LAUNCH("bias_grad_final_kernel");
   }
   return WU_OK;

@@ -710,8 +710,10 @@ __device__ __forceinline__ uint4 keep_mask8(uint32_t thr, uint64_t seed,
   return dropout_keepmask(seed, (uint64_t)vi, thr);
 }
 
-// grid = (ceil(2w * C/8 / 256), B * 2h): one block row per output image row, no index divisions
-// by runtime 64-bit quantities in the hot path.
+// grid = (ceil(2w * C/8 / 256), B * 2h / kRowsPerThread): a thread produces kRowsPerThread
+// consecutive output rows of its (column, 8-channel vector), so 16 independent 16-byte loads are in
+// flight per thread (one output per thread left the kernel latency bound: ~1.3 TB/s).
+constexpr int kRowsPerThread = 4;
 __global__ void __launch_bounds__(256)
 adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ u, int h,
@@ -721,38 +723,54 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
   if (xi >= Wo * cv) return;
   const int X = xi / cv, v = xi - X * cv;
-  const int b = blockIdx.y / Ho, Y = blockIdx.y - b * Ho;
+  const int rows_per_img = (Ho + kRowsPerThread - 1) / kRowsPerThread;
+  const int b = blockIdx.y / rows_per_img;
+  const int Y0 = (blockIdx.y - b * rows_per_img) * kRowsPerThread;
   const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  int y0, y1, x0, x1;
-  float ly, lx;
-  bilinear_src(Y, rh, h, y0, y1, ly);
+  int x0, x1;
+  float lx;
   bilinear_src(X, rw, w, x0, x1, lx);
   const __nv_bfloat16* xb = x + (long long)b * h * w * C + v * 8;
-  float a[8], c[8], d[8], e[8];
-  unpack8(ldg16(xb + ((long long)y0 * w + x0) * C), a);
-  unpack8(ldg16(xb + ((long long)y0 * w + x1) * C), c);
-  unpack8(ldg16(xb + ((long long)y1 * w + x0) * C), d);
-  unpack8(ldg16(xb + ((long long)y1 * w + x1) * C), e);
   const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
   const float4* shp = reinterpret_cast<const float4*>(shift + (long long)b * C + v * 8);
   const float4 sc0 = __ldg(scp), sc1 = __ldg(scp + 1), sh0 = __ldg(shp), sh1 = __ldg(shp + 1);
   const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
   const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-  const long long vi = ((long long)blockIdx.y * Wo + X) * cv + v;
-  const uint4 km = keep_mask8(thr, seed, mask, vi);
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx),
-              w11 = ly * lx;
-  float o[8];
+  uint4 ra[kRowsPerThread], rc[kRowsPerThread], rd[kRowsPerThread], re[kRowsPerThread];
+  float ly[kRowsPerThread];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    // bilinear weights sum to 1, so interpolate x first and apply the affine map once
-    const float xi2 = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
-    o[j] = fmaf(xi2, sc[j], sh[j]) * inv_keep;
+  for (int i = 0; i < kRowsPerThread; ++i) {
+    int y0, y1;
+    bilinear_src(min(Y0 + i, Ho - 1), rh, h, y0, y1, ly[i]);
+    ra[i] = ldg16(xb + ((long long)y0 * w + x0) * C);
+    rc[i] = ldg16(xb + ((long long)y0 * w + x1) * C);
+    rd[i] = ldg16(xb + ((long long)y1 * w + x0) * C);
+    re[i] = ldg16(xb + ((long long)y1 * w + x1) * C);
   }
-  uint4 ov = pack8(o);
-  ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
-  st_stream16(u + vi * 8, ov);
+#pragma unroll
+  for (int i = 0; i < kRowsPerThread; ++i) {
+    if (Y0 + i >= Ho) break;
+    float a[8], c[8], d[8], e[8];
+    unpack8(ra[i], a);
+    unpack8(rc[i], c);
+    unpack8(rd[i], d);
+    unpack8(re[i], e);
+    const long long vi = (((long long)b * Ho + Y0 + i) * Wo + X) * cv + v;
+    const uint4 km = keep_mask8(thr, seed, mask, vi);
+    const float w00 = (1.f - ly[i]) * (1.f - lx), w01 = (1.f - ly[i]) * lx,
+                w10 = ly[i] * (1.f - lx), w11 = ly[i] * lx;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // bilinear weights sum to 1, so interpolate x first and apply the affine map once
+      const float xi2 = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
+      o[j] = fmaf(xi2, sc[j], sh[j]) * inv_keep;
+    }
+    uint4 ov = pack8(o);
+    ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
+    st_stream16(u + vi * 8, ov);
+  }
 }
 
 // Weight with which destination index D contributes to source index s (0 if it does not).
@@ -769,7 +787,7 @@ __device__ __forceinline__ float bilinear_adjoint_w(int D, int s, float ratio, i
 
 // Adjoint of dropout o upsample, separable.  Pass 1 (horizontal, applies the dropout mask):
 //   t[b,Y,x,c] = sum_X wx(X->x) keep(b,Y,X,c)/(1-p) gu[b,Y,X,c],  X in [2x-2, 2x+3]
-// grid = (ceil(w * C/8 / 256), B * 2h).
+// grid = (ceil(w * C/8 / 256), B * 2h / kRowsPerThread); a thread handles kRowsPerThread rows.
 __global__ void __launch_bounds__(256)
 adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ t, int h,
                         int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
@@ -779,25 +797,40 @@ adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __r
   if (xi >= w * cv) return;
   const int xx = xi / cv, v = xi - xx * cv;
   const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const long long row = (long long)blockIdx.y * Wo;  // (b, Y) row of the full-resolution tensor
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float wx[6];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int X = 2 * xx - 2 + j;
-    const float wx = bilinear_adjoint_w(X, xx, rw, w, Wo);
-    if (wx != 0.f) {
-      const long long vi = (row + X) * cv + v;
-      uint4 gv = ld_stream16(gu + vi * 8);
-      const uint4 km = keep_mask8(thr, seed, mask, vi);
-      gv.x &= km.x; gv.y &= km.y; gv.z &= km.z; gv.w &= km.w;
-      float f[8];
-      unpack8(gv, f);
-      const float wgt = wx * inv_keep;
+  for (int j = 0; j < 6; ++j) wx[j] = bilinear_adjoint_w(2 * xx - 2 + j, xx, rw, w, Wo) * inv_keep;
+  const int Ho = 2 * h;
+  const int rows_per_img = (Ho + kRowsPerThread - 1) / kRowsPerThread;
+  const int b = blockIdx.y / rows_per_img;
+  const int Y0 = (blockIdx.y - b * rows_per_img) * kRowsPerThread;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, f[e], acc[e]);
+  for (int i = 0; i < kRowsPerThread; ++i) {
+    if (Y0 + i >= Ho) break;
+    const long long rowi = (long long)b * Ho + Y0 + i;  // (b, Y) row index
+    const long long row = rowi * Wo;
+    uint4 gv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      gv[j] = make_uint4(0, 0, 0, 0);
+      if (wx[j] != 0.f) gv[j] = ld_stream16(gu + ((row + 2 * xx - 2 + j) * cv + v) * 8);
     }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (wx[j] != 0.f) {
+        const long long vi = (row + 2 * xx - 2 + j) * cv + v;
+        const uint4 km = keep_mask8(thr, seed, mask, vi);
+        uint4 g = gv[j];
+        g.x &= km.x; g.y &= km.y; g.z &= km.z; g.w &= km.w;
+        float f[8];
+        unpack8(g, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wx[j], f[e], acc[e]);
+      }
+    }
+    *reinterpret_cast<uint4*>(t + ((rowi * w + xx) * cv + v) * 8) = pack8(acc);
   }
-  *reinterpret_cast<uint4*>(t + (((long long)blockIdx.y * w + xx) * cv + v) * 8) = pack8(acc);
 }
 
 // Pass 2 (vertical) + per-(b,chunk,c) sums S1 = sum gz, S2 = sum gz * xhat:
@@ -1118,10 +1151,10 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
   WU_REQUIRE(x && scale && shift && u && B > 0 && h > 0 && w > 0, "wu_adain_up_drop_fwd: bad args");
   WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_up_drop_fwd: C=%d must be a multiple of 8", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
-  WU_REQUIRE((long long)B * 2 * h <= 65535, "wu_adain_up_drop_fwd: B*2h=%lld exceeds 65535",
-             (long long)B * 2 * h);
+  const long long gy = (long long)B * ((2 * h + kRowsPerThread - 1) / kRowsPerThread);
+  WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_fwd: B*ceil(2h/4)=%lld exceeds 65535", gy);
   const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
-  dim3 grid((unsigned)((2 * w * (C / 8) + 255) / 256), (unsigned)(B * 2 * h));
+  dim3 grid((unsigned)((2 * w * (C / 8) + 255) / 256), (unsigned)gy);
   adain_up_drop_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, scale, shift, (bf16*)u, h, w, C, 1.f / (1.f - p_drop), thr, seed, mask);
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
@@ -1139,13 +1172,13 @@ extern "C" int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* 
              "wu_adain_up_drop_bwd: bad args");
   WU_REQUIRE_ADAIN_C("wu_adain_up_drop_bwd", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_bwd: p_drop=%f out of [0,1)", p_drop);
-  WU_REQUIRE((long long)B * 2 * h <= 65535, "wu_adain_up_drop_bwd: B*2h=%lld exceeds 65535",
-             (long long)B * 2 * h);
+  const long long gy = (long long)B * ((2 * h + kRowsPerThread - 1) / kRowsPerThread);
+  WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_bwd: B*ceil(2h/4)=%lld exceeds 65535", gy);
   const int nchunk = wu_adain_stats_chunks(h * w);
   const int lanes = C / 8, groups = 256 / lanes;
   const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((w * (C / 8) + 255) / 256), (unsigned)(B * 2 * h));
+  dim3 grid((unsigned)((w * (C / 8) + 255) / 256), (unsigned)gy);
   adain_drop_hpass_kernel<<<grid, 256, 0, st>>>((const bf16*)gu, (bf16*)scratch, h, w, C,
                                                 1.f / (1.f - p_drop), thr, seed, mask);
   WU_CHECK_LAUNCH("adain_drop_hpass_kernel");

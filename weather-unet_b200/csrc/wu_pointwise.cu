@@ -74,16 +74,27 @@ bias_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* _
     partial[(size_t)blockIdx.x * C + c] = s;
   }
 }
-__global__ void bias_act_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ db,
-                                          int nblocks, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// db[c] = sum_b partial[b][c]: one block per 32 channels, 8 threads share a channel's block range
+__global__ void __launch_bounds__(256)
+bias_act_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int nblocks,
+                          int C) {
+  __shared__ float red[8][32];
+  const int cl = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * C + c];
-  db[c] = s;
+  if (c < C)
+    for (int b = part; b < nblocks; b += 8) s += partial[(size_t)b * C + c];
+  red[part][cl] = s;
+  __syncthreads();
+  if (part == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cl];
+    db[c] = t;
+  }
 }
 
-constexpr int kBiasActBlocks = 148 * 8;
+constexpr int kBiasActBlocks = 148 * 4;
 
 }  // namespace wu
 
@@ -120,8 +131,8 @@ extern "C" int wu_bias_act_bwd(const void* gy, const void* y, void* g, float* db
       (const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)g, (float*)workspace, slope,
       npix, C);
   WU_CHECK_LAUNCH("bias_act_bwd_kernel");
-  bias_act_bwd_final_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)workspace, db,
-                                                             kBiasActBlocks, C);
+  bias_act_bwd_final_kernel<<<(C + 31) / 32, 256, 0, st>>>((const float*)workspace, db,
+                                                           kBiasActBlocks, C);
   WU_CHECK_LAUNCH("bias_act_bwd_final_kernel");
   return WU_OK;
 }
