@@ -55,6 +55,14 @@ int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int c1, const v
                      const float* bias, int relu, const void* relu_mask_src, void* dst, int cout,
                      int B, int H, int W, wu_stream_t stream);
 
+/* Same, for "one image x many conditions" inference (inference/inf_1year_signals.py:98-107,
+ * dataset.py:200-203): with src1_bcast != 0 the skip source src1 has batch 1 and is shared by all B
+ * images of src0 (its TMA batch coordinate is pinned to 0), so the encoder runs once. */
+int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1, int c1, int src1_bcast,
+                           const void* w_packed, const float* bias, int relu,
+                           const void* relu_mask_src, void* dst, int cout, int B, int H, int W,
+                           wu_stream_t stream);
+
 /* Weight + bias gradient of the same convolution (autograd of nets.py:20,22):
  *   dw[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * src[b,h+r-1,w+s-1,ci]     (fp32, overwritten)
  *   db[co]           = sum_{b,h,w} dy[b,h,w,co]                              (fp32, may be NULL)
@@ -104,16 +112,17 @@ int wu_adain_stats(const void* x, float* partial, int B, int HW, int C, wu_strea
 /* Step 2: style = l1(cond) (utils.py:46) -> y_mean / y_std over the 4 style numbers per channel,
  * combined with the instance statistics into an affine map (all fp32, [B][C]):
  *   mean, rstd = 1/sqrt(var_unbiased + eps), ystd, scale = ystd*rstd, shift = ymean - mean*scale.
- * cond fp32 [B][nc]; lw fp32 [4C][nc]; lb fp32 [4C]. */
+ * cond fp32 [B][nc]; lw fp32 [4C][nc]; lb fp32 [4C].  x_bcast != 0: the statistics (and x in step 3)
+ * have batch 1 and serve all B conditions (one image x many signals). */
 int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, const float* partial,
                        float* mean, float* rstd, float* ystd, float* scale, float* shift, int B,
-                       int C, int nc, int HW, float eps, wu_stream_t stream);
+                       int C, int nc, int HW, float eps, int x_bcast, wu_stream_t stream);
 /* Step 3 (cunet.py:59-61): u[b,Y,X,c] = keep * bilinear_x2(x*scale+shift)[b,Y,X,c] / (1-p).
  * Dropout: p_drop == 0 -> none; else if mask != NULL it is a uint8 NHWC [B][2h][2w][C] keep mask;
  * else keep bits come from a Philox4x32-7 stream keyed by (seed, 8-channel vector index). */
 int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u, int B,
                          int h, int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
-                         wu_stream_t stream);
+                         int x_bcast, wu_stream_t stream);
 /* AdaIN without the fused upsample / dropout (utils.py:49-50 on its own): out = x*scale + shift,
  * scale / shift from wu_adain_style_fwd.  x, out NHWC bf16 [B][HW][C]. */
 int wu_adain_apply(const void* x, const float* scale, const float* shift, void* out, int B, int HW,

@@ -186,3 +186,30 @@ def test_module_surface(cuda):
     y.mean().backward()
     opt.step()
     assert not torch.equal(net(x, c, seed=1), y)
+
+
+def test_one_image_many_conditions(cuda):
+    """inf_1year_signals-style batch (one image x B signals): the encoder-once path gives bit-identical
+    images to the replicated batch, in eval mode and with train-mode dropout (same seed)."""
+    from weather_unet_b200 import _ops as K
+    net = make_net(seed=2).to(cuda)
+    B = 6
+    x1 = torch.rand(1, 3, 64, 96, device=cuda) * 2 - 1
+    c = torch.randn(B, 5, device=cuda)
+    rep = x1.repeat(B, 1, 1, 1)  # materialised copies: the regular path
+    for train in (False, True):
+        net.train(train)
+        with torch.no_grad():
+            n0 = K.launch_count()
+            y_rep = net(rep, c, seed=5)
+            n_rep = K.launch_count() - n0
+            y_exp = net(x1.expand(B, -1, -1, -1), c, seed=5)   # stride-0 batch: detected
+            y_one = net(x1, c, seed=5)                         # explicit (1, ...) image
+        assert torch.equal(y_rep, y_exp) and torch.equal(y_rep, y_one)
+        assert y_one.shape == (B, 3, 64, 96)
+    # with autograd on (training) the regular per-sample path is used and gradients flow
+    net.train()
+    y = net(x1.expand(B, -1, -1, -1), c, seed=5)
+    y.mean().backward()
+    assert net.conv_last.weight.grad is not None
+    assert n_rep > 0

@@ -185,6 +185,43 @@ class _CUNetFn(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
+def transfer_forward(module, x1, c, masks, seed):
+    """One image x many conditions (inference/inf_1year_signals.py:98-107: every batch row is the
+    same image, dataset.py:200-203): the encoder (cunet.py:45-54, 26.8 of 84.8 GFLOP) and the AdaIN
+    statistics of the bottleneck run ONCE on the single image; the decoder runs per condition and
+    reads the skip tensors through a batch-broadcast TMA coordinate.  Bit-identical to running the
+    replicated batch.  Inference only (no autograd graph)."""
+    P = {n: module.get_parameter(n).detach() for n in PARAM_NAMES}
+    packed = module._packed
+    p_drop = module.dropout.p if module.training else 0.0
+    masks = masks or (None, None, None)
+
+    def wf(name):
+        return packed.get(name, P[name])[0]
+
+    def block(src0, src1, name, bcast=False):
+        cout = P[f"{name}.0.weight"].shape[0]
+        a = K.conv3x3(src0, src1, wf(f"{name}.0.weight"), P[f"{name}.0.bias"], True, None, cout,
+                      src1_bcast=bcast)
+        return K.conv3x3(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], True, None, cout)
+
+    a1 = K.conv_first(x1, P["dconv_down1.0.weight"], P["dconv_down1.0.bias"])
+    conv1 = K.conv3x3(a1, None, wf("dconv_down1.2.weight"), P["dconv_down1.2.bias"], True, None, 64)
+    conv2 = block(K.maxpool2(conv1), None, "dconv_down2")
+    conv3 = block(K.maxpool2(conv2), None, "dconv_down3")
+    x4 = block(K.maxpool2(conv3), None, "dconv_down4")
+    u3, _ = K.adain_up_drop(x4, c, P["adain3.l1.weight"], P["adain3.l1.bias"], module.adain3.eps,
+                            p_drop, seed, masks[0], x_bcast=True)
+    h = block(u3, conv3, "dconv_up3", bcast=True)
+    u2, _ = K.adain_up_drop(h, c, P["adain2.l1.weight"], P["adain2.l1.bias"], module.adain2.eps,
+                            p_drop, seed + 1, masks[1])
+    h = block(u2, conv2, "dconv_up2", bcast=True)
+    u1, _ = K.adain_up_drop(h, c, P["adain1.l1.weight"], P["adain1.l1.bias"], module.adain1.eps,
+                            p_drop, seed + 2, masks[2])
+    h = block(u1, conv1, "dconv_up1", bcast=True)
+    return K.conv_last_tanh(h, P["conv_last.weight"], P["conv_last.bias"])
+
+
 def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=None):
     """Host-side checks (utils.py:42 batch assert, cunet.py H%8 requirement) + the autograd node."""
     if x.dim() != 4 or x.shape[1] != 3:
@@ -192,7 +229,13 @@ def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=Non
     if c.dim() != 2 or c.shape[1] != module.num_classes:
         raise ValueError(
             f"Conditional_UNet expects c of shape (B, {module.num_classes}), got {tuple(c.shape)}")
-    assert x.size(0) == c.size(0)  # same failure mode as utils.py:42
+    # one image x many conditions: an explicit (1, 3, H, W) image with B conditions (extension), or
+    # a batch that is a stride-0 expand() of one image — detected for free, no data comparison
+    one_to_many = c.size(0) > 1 and (x.size(0) == 1 or (x.size(0) == c.size(0) and x.stride(0) == 0))
+    if one_to_many and (torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())):
+        one_to_many = False  # training needs per-sample activations: use the regular path
+    if not one_to_many:
+        assert x.size(0) == c.size(0)  # same failure mode as utils.py:42
     if x.shape[2] % 8 or x.shape[3] % 8:
         raise RuntimeError(
             f"Sizes of tensors must match: H and W must be divisible by 8, got {tuple(x.shape[2:])}")
@@ -202,13 +245,17 @@ def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=Non
     if x.requires_grad or c.requires_grad:
         raise RuntimeError("weather-unet_b200: gradients w.r.t. x or c are not provided "
                            "(the reference trains the generator's parameters only)")
+    if one_to_many and keep_acts is None:
+        x = x[:1]  # never materialise the replicated batch
+    elif x.size(0) == 1 and c.size(0) > 1:
+        x = x.expand(c.size(0), -1, -1, -1)
     x = x.detach().contiguous().float()
     c = c.detach().contiguous().float()
     training = module.training
     masks = None
     if dropout_masks is not None:
         masks = tuple(m.contiguous() for m in dropout_masks)
-        B, H, W = x.shape[0], x.shape[2], x.shape[3]
+        B, H, W = c.shape[0], x.shape[2], x.shape[3]
         want = [(B, H // 4, W // 4, 512), (B, H // 2, W // 2, 256), (B, H, W, 128)]
         for m, s in zip(masks, want):
             if tuple(m.shape) != s or m.dtype != torch.uint8:
@@ -216,6 +263,8 @@ def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=Non
     if seed is None:
         # host RNG draw (no device sync); three sites use seed, seed+1, seed+2
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+    if one_to_many and keep_acts is None:
+        return transfer_forward(module, x, c, masks, seed)
     params = [module.get_parameter(n) for n in PARAM_NAMES]
     opts = dict(training=training, p=module.dropout.p, masks=masks, seed=seed,
                 eps=(module.adain3.eps, module.adain2.eps, module.adain1.eps),

@@ -23,6 +23,7 @@ SIGNATURES = {
     "wu_launch_count": (c_ulonglong, []),
     "wu_pack_conv3x3_weights": (I, [P, I, I, P, P, P]),
     "wu_conv3x3_fprop": (I, [P, I, P, I, P, P, I, P, P, I, I, I, I, P]),
+    "wu_conv3x3_fprop_bcast": (I, [P, I, P, I, I, P, P, I, P, P, I, I, I, I, P]),
     "wu_conv3x3_wgrad_workspace_bytes": (SZ, [I, I, I, I, I]),
     "wu_conv3x3_wgrad": (I, [P, I, P, I, P, I, I, I, I, P, P, P, SZ, P]),
     "wu_conv_first_fprop": (I, [P, P, P, P, I, I, I, P]),
@@ -35,9 +36,9 @@ SIGNATURES = {
     "wu_maxpool2_bwd": (I, [P, P, P, P, I, I, I, I, P]),
     "wu_adain_stats_chunks": (I, [I]),
     "wu_adain_stats": (I, [P, P, I, I, I, P]),
-    "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, P]),
+    "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "wu_adain_apply": (I, [P, P, P, P, I, I, I, P]),
-    "wu_adain_up_drop_fwd": (I, [P, P, P, P, I, I, I, I, F, U64, P, P]),
+    "wu_adain_up_drop_fwd": (I, [P, P, P, P, I, I, I, I, F, U64, P, I, P]),
     "wu_adain_up_drop_bwd_scratch_bytes": (SZ, [I, I, I, I]),
     "wu_adain_up_drop_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, U64, P, P]),
     "wu_adain_style_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),

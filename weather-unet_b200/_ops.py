@@ -25,13 +25,14 @@ def pack_conv3x3_weights(w, need_dgrad=True):
     return wf, wd
 
 
-def conv3x3(src0, src1, w_packed, bias, relu, mask, cout):
-    """3x3/s1/p1 convolution over the (virtual) channel concat [src0, src1]; see wu_conv3x3_fprop."""
+def conv3x3(src0, src1, w_packed, bias, relu, mask, cout, src1_bcast=False):
+    """3x3/s1/p1 convolution over the (virtual) channel concat [src0, src1]; see wu_conv3x3_fprop.
+    src1_bcast: src1 has batch 1 and is shared by every image of src0."""
     B, H, W, c0 = src0.shape
     c1 = 0 if src1 is None else src1.shape[3]
     dst = _act(B, H, W, cout, src0)
-    call("wu_conv3x3_fprop", ptr(src0), c0, ptr(src1), c1, ptr(w_packed), ptr(bias), int(relu),
-         ptr(mask), ptr(dst), cout, B, H, W, stream())
+    call("wu_conv3x3_fprop_bcast", ptr(src0), c0, ptr(src1), c1, int(src1_bcast), ptr(w_packed),
+         ptr(bias), int(relu), ptr(mask), ptr(dst), cout, B, H, W, stream())
     return dst
 
 
@@ -107,23 +108,26 @@ class AdaINState:
     __slots__ = ("mean", "rstd", "ystd", "scale", "shift", "seed", "mask", "p")
 
 
-def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask):
-    """AdaIN(x, cond) -> bilinear x2 (align_corners) -> dropout.  x (B,h,w,C) -> (B,2h,2w,C)."""
-    B, h, w, C = x.shape
+def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False):
+    """AdaIN(x, cond) -> bilinear x2 (align_corners) -> dropout.  x (B,h,w,C) -> (B,2h,2w,C).
+    x_bcast: x has batch 1 and serves all cond.shape[0] conditions."""
+    Bx, h, w, C = x.shape
+    B = cond.shape[0] if x_bcast else Bx
     nc = cond.shape[1]
     nchunk = query("wu_adain_stats_chunks", h * w)
     dev = x.device
-    partial = torch.empty((B, nchunk, C, 2), dtype=torch.float32, device=dev)
-    call("wu_adain_stats", ptr(x), ptr(partial), B, h * w, C, stream())
+    partial = torch.empty((Bx, nchunk, C, 2), dtype=torch.float32, device=dev)
+    call("wu_adain_stats", ptr(x), ptr(partial), Bx, h * w, C, stream())
     st = AdaINState()
     buf = torch.empty((5, B, C), dtype=torch.float32, device=dev)
     st.mean, st.rstd, st.ystd, st.scale, st.shift = buf[0], buf[1], buf[2], buf[3], buf[4]
     st.seed, st.mask, st.p = int(seed), mask, float(p_drop)
     call("wu_adain_style_fwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.mean), ptr(st.rstd),
-         ptr(st.ystd), ptr(st.scale), ptr(st.shift), B, C, nc, h * w, float(eps), stream())
+         ptr(st.ystd), ptr(st.scale), ptr(st.shift), B, C, nc, h * w, float(eps), int(x_bcast),
+         stream())
     u = _act(B, 2 * h, 2 * w, C, x)
     call("wu_adain_up_drop_fwd", ptr(x), ptr(st.scale), ptr(st.shift), ptr(u), B, h, w, C, st.p,
-         st.seed, ptr(mask), stream())
+         st.seed, ptr(mask), int(x_bcast), stream())
     return u, st
 
 
@@ -137,7 +141,7 @@ def adain_apply(x, cond, lw, lb, eps):
     call("wu_adain_stats", ptr(x), ptr(partial), B, h * w, C, stream())
     buf = torch.empty((5, B, C), dtype=torch.float32, device=dev)
     call("wu_adain_style_fwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(buf[0]), ptr(buf[1]),
-         ptr(buf[2]), ptr(buf[3]), ptr(buf[4]), B, C, nc, h * w, float(eps), stream())
+         ptr(buf[2]), ptr(buf[3]), ptr(buf[4]), B, C, nc, h * w, float(eps), 0, stream())
     out = torch.empty_like(x)
     call("wu_adain_apply", ptr(x), ptr(buf[3]), ptr(buf[4]), ptr(out), B, h * w, C, stream())
     return out

@@ -34,6 +34,7 @@ struct ConvParams {
   int num_tiles;  // batch * tiles_h * tiles_w * n_tiles
   int H, W, cout;
   int relu;
+  int b1_mul;                 // 1, or 0 when source 1 has batch 1 and is shared by every image
   const float* bias;          // [cout] or null
   const __nv_bfloat16* mask;  // NHWC [B][H][W][cout] or null: dst = mask > 0 ? dst : 0
 };
@@ -209,7 +210,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
               tma_load_4d(a_dst, &tmA0, fb, cb * 64, t.w0 + s - 1, t.h0 + r - 1, t.b);
             else
               tma_load_4d(a_dst, &tmA1, fb, (cb - p.c0_blocks) * 64, t.w0 + s - 1, t.h0 + r - 1,
-                          t.b);
+                          t.b * p.b1_mul);
             tma_load_2d(b_dst, &tmB, fb, (tap * p.ctot_blocks + cb) * 64, t.n0);
             if (++stage == S) {
               stage = 0;
@@ -350,6 +351,7 @@ struct ConvParams2 {
   int tiles_w, tiles_h, batch;
   int n_tiles, num_tiles;
   int H, W, cout, relu;
+  int b1_mul;  // 1, or 0 when source 1 has batch 1 and is shared by every image
   const float* bias;
   const __nv_bfloat16* mask;
 };
@@ -453,7 +455,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
               tma_load_4d(a_base + sa * Cfg::kABytes, &tmA0, fullA(sa), cb * 64, w0 + s - 1, h0 - 1, b);
             else
               tma_load_4d(a_base + sa * Cfg::kABytes, &tmA1, fullA(sa), (cb - p.c0_blocks) * 64,
-                          w0 + s - 1, h0 - 1, b);
+                          w0 + s - 1, h0 - 1, b * p.b1_mul);
             if (++sa == SA) { sa = 0; pa ^= 1u; }
             for (int r = 0; r < 3; ++r) {
               mbar_wait(emptyB(sb), pb ^ 1u);
@@ -1263,6 +1265,14 @@ extern "C" int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int 
                                 const void* w_packed, const float* bias, int relu,
                                 const void* relu_mask_src, void* dst, int cout, int B, int H, int W,
                                 wu_stream_t stream) {
+  return wu_conv3x3_fprop_bcast(src0, c0, src1, c1, 0, w_packed, bias, relu, relu_mask_src, dst, cout,
+                                B, H, W, stream);
+}
+
+extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1, int c1,
+                                      int src1_bcast, const void* w_packed, const float* bias,
+                                      int relu, const void* relu_mask_src, void* dst, int cout,
+                                      int B, int H, int W, wu_stream_t stream) {
   WU_REQUIRE(src0 && w_packed && dst, "wu_conv3x3_fprop: null pointer");
   WU_REQUIRE(B > 0 && H > 0 && W > 0, "wu_conv3x3_fprop: bad shape B=%d H=%d W=%d", B, H, W);
   WU_REQUIRE(c0 > 0 && c0 % 64 == 0, "wu_conv3x3_fprop: c0=%d must be a positive multiple of 64", c0);
@@ -1287,13 +1297,15 @@ extern "C" int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int 
     q.W = W;
     q.cout = cout;
     q.relu = relu;
+    q.b1_mul = src1_bcast ? 0 : 1;
     q.bias = bias;
     q.mask = (const __nv_bfloat16*)relu_mask_src;
     CUtensorMap a0, a1, bm, dm;
     int rc;
     if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, 8, 16 * T + 2)) != WU_OK) return rc;
     if (c1 > 0) {
-      if ((rc = make_act_tmap(&a1, src1, B, H, W, c1, c1, 8, 16 * T + 2)) != WU_OK) return rc;
+      if ((rc = make_act_tmap(&a1, src1, src1_bcast ? 1 : B, H, W, c1, c1, 8, 16 * T + 2)) != WU_OK)
+        return rc;
     } else {
       a1 = a0;
     }
@@ -1322,13 +1334,15 @@ extern "C" int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int 
   p.W = W;
   p.cout = cout;
   p.relu = relu;
+  p.b1_mul = src1_bcast ? 0 : 1;
   p.bias = bias;
   p.mask = (const __nv_bfloat16*)relu_mask_src;
   CUtensorMap a0, a1, bm, dm;
   int rc;
   if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, p.bw, p.bh)) != WU_OK) return rc;
   if (c1 > 0) {
-    if ((rc = make_act_tmap(&a1, src1, B, H, W, c1, c1, p.bw, p.bh)) != WU_OK) return rc;
+    if ((rc = make_act_tmap(&a1, src1, src1_bcast ? 1 : B, H, W, c1, c1, p.bw, p.bh)) != WU_OK)
+      return rc;
   } else {
     a1 = a0;
   }

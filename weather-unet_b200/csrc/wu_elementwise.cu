@@ -649,10 +649,11 @@ __global__ void adain_style_fwd_kernel(const float* __restrict__ cond, const flo
                                        const float* __restrict__ partial, float* __restrict__ mean,
                                        float* __restrict__ rstd, float* __restrict__ ystd,
                                        float* __restrict__ scale, float* __restrict__ shift, int B,
-                                       int C, int nc, int HW, int nchunk, float eps) {
+                                       int C, int nc, int HW, int nchunk, float eps, int xb_mul) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
+  const int bx = b * xb_mul;  // batch index of the statistics (0 when one x serves every condition)
   float h[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -667,7 +668,7 @@ __global__ void adain_style_fwd_kernel(const float* __restrict__ cond, const flo
   const float ys = sqrtf(yv * (1.f / 3.f) + eps);
   double s1 = 0.0, s2 = 0.0;
   for (int k = 0; k < nchunk; ++k) {
-    const float* pp = partial + (((size_t)b * nchunk + k) * C + c) * 2;
+    const float* pp = partial + (((size_t)bx * nchunk + k) * C + c) * 2;
     s1 += (double)pp[0];
     s2 += (double)pp[1];
   }
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(256)
 adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ u, int h,
                          int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
-                         const uint8_t* __restrict__ mask) {
+                         const uint8_t* __restrict__ mask, int xb_mul) {
   const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
   if (xi >= Wo * cv) return;
@@ -731,7 +732,7 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   int x0, x1;
   float lx;
   bilinear_src(X, rw, w, x0, x1, lx);
-  const __nv_bfloat16* xb = x + (long long)b * h * w * C + v * 8;
+  const __nv_bfloat16* xb = x + (long long)(b * xb_mul) * h * w * C + v * 8;
   const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
   const float4* shp = reinterpret_cast<const float4*>(shift + (long long)b * C + v * 8);
   const float4 sc0 = __ldg(scp), sc1 = __ldg(scp + 1), sh0 = __ldg(shp), sh1 = __ldg(shp + 1);
@@ -1135,19 +1136,19 @@ extern "C" int wu_adain_stats(const void* x, float* partial, int B, int HW, int 
 extern "C" int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb,
                                   const float* partial, float* mean, float* rstd, float* ystd,
                                   float* scale, float* shift, int B, int C, int nc, int HW,
-                                  float eps, wu_stream_t stream) {
+                                  float eps, int x_bcast, wu_stream_t stream) {
   WU_REQUIRE(cond && lw && lb && partial && mean && rstd && ystd && scale && shift,
              "wu_adain_style_fwd: null pointer");
   WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0, "wu_adain_style_fwd: bad shape");
   adain_style_fwd_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       cond, lw, lb, partial, mean, rstd, ystd, scale, shift, B, C, nc, HW,
-      wu_adain_stats_chunks(HW), eps);
+      wu_adain_stats_chunks(HW), eps, x_bcast ? 0 : 1);
   WU_CHECK_LAUNCH("adain_style_fwd_kernel");
   return WU_OK;
 }
 extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u,
                                     int B, int h, int w, int C, float p_drop, uint64_t seed,
-                                    const uint8_t* mask, wu_stream_t stream) {
+                                    const uint8_t* mask, int x_bcast, wu_stream_t stream) {
   WU_REQUIRE(x && scale && shift && u && B > 0 && h > 0 && w > 0, "wu_adain_up_drop_fwd: bad args");
   WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_up_drop_fwd: C=%d must be a multiple of 8", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
@@ -1156,7 +1157,8 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
   const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
   dim3 grid((unsigned)((2 * w * (C / 8) + 255) / 256), (unsigned)gy);
   adain_up_drop_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, scale, shift, (bf16*)u, h, w, C, 1.f / (1.f - p_drop), thr, seed, mask);
+      (const bf16*)x, scale, shift, (bf16*)u, h, w, C, 1.f / (1.f - p_drop), thr, seed, mask,
+      x_bcast ? 0 : 1);
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
   return WU_OK;
 }
