@@ -119,10 +119,12 @@ int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, cons
                        int C, int nc, int HW, float eps, int x_bcast, wu_stream_t stream);
 /* Step 3 (cunet.py:59-61): u[b,Y,X,c] = keep * bilinear_x2(x*scale+shift)[b,Y,X,c] / (1-p).
  * Dropout: p_drop == 0 -> none; else if mask != NULL it is a uint8 NHWC [B][2h][2w][C] keep mask;
- * else keep bits come from a Philox4x32-7 stream keyed by (seed, 8-channel vector index). */
-int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u, int B,
-                         int h, int w, int C, float p_drop, uint64_t seed, const uint8_t* mask,
-                         int x_bcast, wu_stream_t stream);
+ * else keep bits come from a Philox4x32-7 stream keyed by (seed, 8-channel vector index).
+ * keep_bits (required when p_drop > 0): uint8 [B][2h][2w][C/8], bit j = channel 8v+j kept; the
+ * backward pass reads it instead of replaying the RNG. */
+int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u,
+                         uint8_t* keep_bits, int B, int h, int w, int C, float p_drop, uint64_t seed,
+                         const uint8_t* mask, int x_bcast, wu_stream_t stream);
 /* AdaIN without the fused upsample / dropout (utils.py:49-50 on its own): out = x*scale + shift,
  * scale / shift from wu_adain_style_fwd.  x, out NHWC bf16 [B][HW][C]. */
 int wu_adain_apply(const void* x, const float* scale, const float* shift, void* out, int B, int HW,
@@ -135,17 +137,19 @@ int wu_adain_apply(const void* x, const float* scale, const float* shift, void* 
 size_t wu_adain_up_drop_bwd_scratch_bytes(int B, int h, int w, int C);
 int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean, const float* rstd,
                          void* gz, float* partial, void* scratch, int B, int h, int w, int C,
-                         float p_drop, uint64_t seed, const uint8_t* mask, wu_stream_t stream);
-/* Backward, step 2: reduce the partials, emit k1 = S1/N and k2 = S2/(N-1) ([B][C] fp32) and the
+                         float p_drop, const uint8_t* keep_bits, wu_stream_t stream);
+/* Backward, step 2: reduce the partials, emit k1 = S1/N and k2 = S2/(N-1) ([B][C] fp32), the apply
+ * coefficients coef fp32 [3][B][C] (A = rstd*ystd, Bc = -A*k2*rstd, Cc = A*(k2*rstd*mean - k1)) and the
  * gradients of l1.weight / l1.bias (utils.py:31,46), overwritten: dlw [4C][nc], dlb [4C].
  * gh is caller scratch, fp32 [B][4C] (gradient of the style vector l1(cond)). */
 int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb, const float* partial,
-                       const float* ystd, float* k1, float* k2, float* gh, float* dlw, float* dlb,
-                       int B, int C, int nc, int HW, wu_stream_t stream);
-/* Backward, step 3: gx = relu'(x) * rstd*ystd * (gz - k1 - xhat*k2), bf16 [B][h][w][C]. */
-int wu_adain_bwd_apply(const void* gz, const void* x, const float* mean, const float* rstd,
-                       const float* ystd, const float* k1, const float* k2, void* gx, int B,
-                       int HW, int C, wu_stream_t stream);
+                       const float* ystd, const float* mean, const float* rstd, float* k1, float* k2,
+                       float* coef, float* gh, float* dlw, float* dlb, int B, int C, int nc, int HW,
+                       wu_stream_t stream);
+/* Backward, step 3: gx = relu'(x) * (A*gz + Bc*x + Cc)  ==  relu'(x) * rstd*ystd*(gz - k1 - xhat*k2),
+ * bf16 [B][h][w][C]. */
+int wu_adain_bwd_apply(const void* gz, const void* x, const float* coef, void* gx, int B, int HW,
+                       int C, wu_stream_t stream);
 
 /* ---- bias + LeakyReLU on NHWC bf16 (discriminator blocks, nets.py:26-33) ---------
  * fwd, in place: x = leaky_relu(x + bias[c], slope); slope == 1 is a plain bias add.

@@ -105,7 +105,7 @@ def maxpool2_bwd(y, g_pool, g_skip):
 
 class AdaINState:
     """Per-call statistics of one AdaIN site kept for the backward pass (all fp32 [B][C])."""
-    __slots__ = ("mean", "rstd", "ystd", "scale", "shift", "seed", "mask", "p")
+    __slots__ = ("mean", "rstd", "ystd", "scale", "shift", "seed", "mask", "p", "bits")
 
 
 def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False):
@@ -126,8 +126,10 @@ def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False):
          ptr(st.ystd), ptr(st.scale), ptr(st.shift), B, C, nc, h * w, float(eps), int(x_bcast),
          stream())
     u = _act(B, 2 * h, 2 * w, C, x)
-    call("wu_adain_up_drop_fwd", ptr(x), ptr(st.scale), ptr(st.shift), ptr(u), B, h, w, C, st.p,
-         st.seed, ptr(mask), int(x_bcast), stream())
+    st.bits = (torch.empty((B, 2 * h, 2 * w, C // 8), dtype=torch.uint8, device=dev)
+               if st.p > 0 else None)
+    call("wu_adain_up_drop_fwd", ptr(x), ptr(st.scale), ptr(st.shift), ptr(u), ptr(st.bits), B, h, w,
+         C, st.p, st.seed, ptr(mask), int(x_bcast), stream())
     return u, st
 
 
@@ -157,16 +159,16 @@ def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
     gz = torch.empty_like(x)
     scratch = torch.empty((B, 2 * h, w, C), dtype=BF16, device=dev)
     call("wu_adain_up_drop_bwd", ptr(gu), ptr(x), ptr(st.mean), ptr(st.rstd), ptr(gz), ptr(partial),
-         ptr(scratch), B, h, w, C, st.p, st.seed, ptr(st.mask), stream())
-    kk = torch.empty((2, B, C), dtype=torch.float32, device=dev)
+         ptr(scratch), B, h, w, C, st.p, ptr(st.bits), stream())
+    kk = torch.empty((5, B, C), dtype=torch.float32, device=dev)  # k1, k2, coef[3]
     gh = torch.empty((B, 4 * C), dtype=torch.float32, device=dev)
     dlw = torch.empty((4 * C, nc), dtype=torch.float32, device=dev)
     dlb = torch.empty((4 * C,), dtype=torch.float32, device=dev)
-    call("wu_adain_style_bwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.ystd), ptr(kk[0]),
-         ptr(kk[1]), ptr(gh), ptr(dlw), ptr(dlb), B, C, nc, h * w, stream())
+    call("wu_adain_style_bwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.ystd), ptr(st.mean),
+         ptr(st.rstd), ptr(kk[0]), ptr(kk[1]), ptr(kk[2]), ptr(gh), ptr(dlw), ptr(dlb), B, C, nc, h * w,
+         stream())
     gx = torch.empty_like(x)
-    call("wu_adain_bwd_apply", ptr(gz), ptr(x), ptr(st.mean), ptr(st.rstd), ptr(st.ystd), ptr(kk[0]),
-         ptr(kk[1]), ptr(gx), B, h * w, C, stream())
+    call("wu_adain_bwd_apply", ptr(gz), ptr(x), ptr(kk[2]), ptr(gx), B, h * w, C, stream())
     return gx, dlw, dlb
 
 

@@ -697,11 +697,27 @@ __device__ __forceinline__ void bilinear_src(int dst, float ratio, int in, int& 
   lam = s - (float)i0;
 }
 
-// keep mask (packed bf16x2 lanes) for 8 consecutive channels: injected uint8 mask or Philox stream
+// Dropout keep decisions of one 8-channel vector as a byte (bit j = channel j) and as packed
+// bf16x2 lane masks.  The forward pass decides (Philox stream or injected uint8 mask) and stores the
+// byte; the backward pass only reads bytes back (1/16 of the activation bytes, no RNG replay).
+enum { kDropNone = 0, kDropPhilox = 1, kDropInjected = 2 };
+
+__device__ __forceinline__ uint32_t lanes_to_byte(const uint4& km) {
+  return (km.x & 1u) | ((km.x >> 15) & 2u) | ((km.y & 1u) << 2) | ((km.y >> 13) & 8u) |
+         ((km.z & 1u) << 4) | ((km.z >> 11) & 32u) | ((km.w & 1u) << 6) | ((km.w >> 9) & 128u);
+}
+__device__ __forceinline__ uint32_t byte_pair_to_lanes(uint32_t two_bits) {
+  return ((two_bits & 1u) ? 0x0000FFFFu : 0u) | ((two_bits & 2u) ? 0xFFFF0000u : 0u);
+}
+__device__ __forceinline__ uint4 byte_to_lanes(uint32_t b) {
+  return make_uint4(byte_pair_to_lanes(b), byte_pair_to_lanes(b >> 2), byte_pair_to_lanes(b >> 4),
+                    byte_pair_to_lanes(b >> 6));
+}
+template <int MODE>
 __device__ __forceinline__ uint4 keep_mask8(uint32_t thr, uint64_t seed,
                                             const uint8_t* __restrict__ mask, long long vi) {
-  if (thr == 0u) return make_uint4(~0u, ~0u, ~0u, ~0u);
-  if (mask != nullptr) {
+  if (MODE == kDropNone) return make_uint4(~0u, ~0u, ~0u, ~0u);
+  if (MODE == kDropInjected) {
     const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mask + vi * 8));
     auto lanes = [](uint32_t two_bytes) -> uint32_t {
       return ((two_bytes & 0xFFu) ? 0x0000FFFFu : 0u) | ((two_bytes & 0xFF00u) ? 0xFFFF0000u : 0u);
@@ -711,15 +727,17 @@ __device__ __forceinline__ uint4 keep_mask8(uint32_t thr, uint64_t seed,
   return dropout_keepmask(seed, (uint64_t)vi, thr);
 }
 
-// grid = (ceil(2w * C/8 / 256), B * 2h / kRowsPerThread): a thread produces kRowsPerThread
+// grid = (ceil(2w * C/8 / 256), B * ceil(2h / kRowsPerThread)): a thread produces kRowsPerThread
 // consecutive output rows of its (column, 8-channel vector), so 16 independent 16-byte loads are in
-// flight per thread (one output per thread left the kernel latency bound: ~1.3 TB/s).
+// flight per thread.  The kernel is instruction bound (RNG + interpolation per 16 output bytes), so
+// the dropout mode is a template parameter and all row-invariant index math is hoisted.
 constexpr int kRowsPerThread = 4;
+template <int MODE>
 __global__ void __launch_bounds__(256)
 adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
-                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ u, int h,
-                         int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
-                         const uint8_t* __restrict__ mask, int xb_mul) {
+                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ u,
+                         uint8_t* __restrict__ keep_bits, int h, int w, int C, float inv_keep,
+                         uint32_t thr, uint64_t seed, const uint8_t* __restrict__ mask, int xb_mul) {
   const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
   if (xi >= Wo * cv) return;
@@ -733,43 +751,52 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   float lx;
   bilinear_src(X, rw, w, x0, x1, lx);
   const __nv_bfloat16* xb = x + (long long)(b * xb_mul) * h * w * C + v * 8;
+  const int o0 = x0 * C, o1 = x1 * C, row_pitch = w * C;  // 32-bit offsets inside one image
   const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
   const float4* shp = reinterpret_cast<const float4*>(shift + (long long)b * C + v * 8);
   const float4 sc0 = __ldg(scp), sc1 = __ldg(scp + 1), sh0 = __ldg(shp), sh1 = __ldg(shp + 1);
-  const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-  const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+  const float sc[8] = {sc0.x * inv_keep, sc0.y * inv_keep, sc0.z * inv_keep, sc0.w * inv_keep,
+                       sc1.x * inv_keep, sc1.y * inv_keep, sc1.z * inv_keep, sc1.w * inv_keep};
+  const float sh[8] = {sh0.x * inv_keep, sh0.y * inv_keep, sh0.z * inv_keep, sh0.w * inv_keep,
+                       sh1.x * inv_keep, sh1.y * inv_keep, sh1.z * inv_keep, sh1.w * inv_keep};
   uint4 ra[kRowsPerThread], rc[kRowsPerThread], rd[kRowsPerThread], re[kRowsPerThread];
   float ly[kRowsPerThread];
 #pragma unroll
   for (int i = 0; i < kRowsPerThread; ++i) {
     int y0, y1;
     bilinear_src(min(Y0 + i, Ho - 1), rh, h, y0, y1, ly[i]);
-    ra[i] = ldg16(xb + ((long long)y0 * w + x0) * C);
-    rc[i] = ldg16(xb + ((long long)y0 * w + x1) * C);
-    rd[i] = ldg16(xb + ((long long)y1 * w + x0) * C);
-    re[i] = ldg16(xb + ((long long)y1 * w + x1) * C);
+    const __nv_bfloat16* r0 = xb + y0 * row_pitch;
+    const __nv_bfloat16* r1 = xb + y1 * row_pitch;
+    ra[i] = ldg16(r0 + o0);
+    rc[i] = ldg16(r0 + o1);
+    rd[i] = ldg16(r1 + o0);
+    re[i] = ldg16(r1 + o1);
   }
+  long long vi = (((long long)b * Ho + Y0) * Wo + X) * cv + v;
+  const long long vi_row = (long long)Wo * cv;
 #pragma unroll
-  for (int i = 0; i < kRowsPerThread; ++i) {
+  for (int i = 0; i < kRowsPerThread; ++i, vi += vi_row) {
     if (Y0 + i >= Ho) break;
     float a[8], c[8], d[8], e[8];
     unpack8(ra[i], a);
     unpack8(rc[i], c);
     unpack8(rd[i], d);
     unpack8(re[i], e);
-    const long long vi = (((long long)b * Ho + Y0 + i) * Wo + X) * cv + v;
-    const uint4 km = keep_mask8(thr, seed, mask, vi);
+    const uint4 km = keep_mask8<MODE>(thr, seed, mask, vi);
     const float w00 = (1.f - ly[i]) * (1.f - lx), w01 = (1.f - ly[i]) * lx,
                 w10 = ly[i] * (1.f - lx), w11 = ly[i] * lx;
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      // bilinear weights sum to 1, so interpolate x first and apply the affine map once
+      // bilinear weights sum to 1: interpolate x, then one fused affine map (1/(1-p) folded in)
       const float xi2 = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
-      o[j] = fmaf(xi2, sc[j], sh[j]) * inv_keep;
+      o[j] = fmaf(xi2, sc[j], sh[j]);
     }
     uint4 ov = pack8(o);
-    ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
+    if (MODE != kDropNone) {
+      ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
+      keep_bits[vi] = (uint8_t)lanes_to_byte(km);
+    }
     st_stream16(u + vi * 8, ov);
   }
 }
@@ -788,11 +815,11 @@ __device__ __forceinline__ float bilinear_adjoint_w(int D, int s, float ratio, i
 
 // Adjoint of dropout o upsample, separable.  Pass 1 (horizontal, applies the dropout mask):
 //   t[b,Y,x,c] = sum_X wx(X->x) keep(b,Y,X,c)/(1-p) gu[b,Y,X,c],  X in [2x-2, 2x+3]
-// grid = (ceil(w * C/8 / 256), B * 2h / kRowsPerThread); a thread handles kRowsPerThread rows.
+// keep comes from the byte tensor the forward pass stored (keep_bits == nullptr: no dropout).
+// grid = (ceil(w * C/8 / 256), B * ceil(2h / kRowsPerThread)); a thread handles kRowsPerThread rows.
 __global__ void __launch_bounds__(256)
-adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ t, int h,
-                        int w, int C, float inv_keep, uint32_t thr, uint64_t seed,
-                        const uint8_t* __restrict__ mask) {
+adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ t,
+                        const uint8_t* __restrict__ keep_bits, int h, int w, int C, float inv_keep) {
   const int cv = C >> 3, Wo = 2 * w;
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
   if (xi >= w * cv) return;
@@ -809,19 +836,23 @@ adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __r
   for (int i = 0; i < kRowsPerThread; ++i) {
     if (Y0 + i >= Ho) break;
     const long long rowi = (long long)b * Ho + Y0 + i;  // (b, Y) row index
-    const long long row = rowi * Wo;
+    const long long vbase = (rowi * Wo + 2 * xx - 2) * cv + v;
     uint4 gv[6];
+    uint32_t kb[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       gv[j] = make_uint4(0, 0, 0, 0);
-      if (wx[j] != 0.f) gv[j] = ld_stream16(gu + ((row + 2 * xx - 2 + j) * cv + v) * 8);
+      kb[j] = 0xFFu;
+      if (wx[j] != 0.f) {
+        gv[j] = ld_stream16(gu + (vbase + (long long)j * cv) * 8);
+        if (keep_bits != nullptr) kb[j] = __ldg(keep_bits + vbase + (long long)j * cv);
+      }
     }
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       if (wx[j] != 0.f) {
-        const long long vi = (row + 2 * xx - 2 + j) * cv + v;
-        const uint4 km = keep_mask8(thr, seed, mask, vi);
+        const uint4 km = byte_to_lanes(kb[j]);
         uint4 g = gv[j];
         g.x &= km.x; g.y &= km.y; g.z &= km.z; g.w &= km.w;
         float f[8];
@@ -890,9 +921,12 @@ adain_up_vpass_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* 
 __global__ void adain_style_bwd_kernel(const float* __restrict__ cond, const float* __restrict__ lw,
                                        const float* __restrict__ lb,
                                        const float* __restrict__ partial,
-                                       const float* __restrict__ ystd, float* __restrict__ k1,
-                                       float* __restrict__ k2, float* __restrict__ gh, int B, int C,
-                                       int nc, int HW, int nchunk) {
+                                       const float* __restrict__ ystd,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, float* __restrict__ k1,
+                                       float* __restrict__ k2, float* __restrict__ coef,
+                                       float* __restrict__ gh, int B, int C, int nc, int HW,
+                                       int nchunk) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
@@ -902,8 +936,16 @@ __global__ void adain_style_bwd_kernel(const float* __restrict__ cond, const flo
     s1 += (double)pp[0];
     s2 += (double)pp[1];
   }
-  k1[i] = (float)(s1 / HW);
-  k2[i] = (float)(s2 / (HW > 1 ? HW - 1 : 1));
+  const float kk1 = (float)(s1 / HW), kk2 = (float)(s2 / (HW > 1 ? HW - 1 : 1));
+  k1[i] = kk1;
+  k2[i] = kk2;
+  {
+    // gx = relu'(x) * rstd*ystd * (gz - k1 - xhat*k2) = relu'(x) * (A*gz + Bc*x + Cc)
+    const float r = rstd[i], A = r * ystd[i];
+    coef[i] = A;
+    coef[(size_t)B * C + i] = -A * kk2 * r;
+    coef[2 * (size_t)B * C + i] = A * (kk2 * r * mean[i] - kk1);
+  }
   float h[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -955,30 +997,31 @@ adain_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   }
 }
 
-// gx = (x > 0) * rstd * ystd * (gz - k1 - xhat * k2)
+// gx = (x > 0) * (A*gz + Bc*x + Cc), coefficients per (b, c) from adain_style_bwd_kernel
 __global__ void __launch_bounds__(256)
 adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ gz, const __nv_bfloat16* __restrict__ x,
-                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                       const float* __restrict__ ystd, const float* __restrict__ k1,
-                       const float* __restrict__ k2, __nv_bfloat16* __restrict__ gx, int B, int HW,
+                       const float* __restrict__ coef, __nv_bfloat16* __restrict__ gx, int B, int HW,
                        int C) {
   const int cv = C >> 3;
   const long long total = (long long)B * HW * cv;
+  const size_t plane = (size_t)B * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
     const int b = (int)(i / ((long long)HW * cv));
-    const long long pc = (long long)b * C + v * 8;
+    const float4* cp = reinterpret_cast<const float4*>(coef + (size_t)b * C + v * 8);
+    const float4 a0 = __ldg(cp), a1 = __ldg(cp + 1);
+    const float4 b0 = __ldg(cp + plane / 4), b1 = __ldg(cp + plane / 4 + 1);
+    const float4 c0 = __ldg(cp + plane / 2), c1 = __ldg(cp + plane / 2 + 1);
+    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float Bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float Cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
     float g[8], xv[8], o[8];
     unpack8(ld_stream16(gz + i * 8), g);
     unpack8(ld_stream16(x + i * 8), xv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float r = __ldg(rstd + pc + j);
-      const float xh = (xv[j] - __ldg(mean + pc + j)) * r;
-      const float val = r * __ldg(ystd + pc + j) * (g[j] - __ldg(k1 + pc + j) - xh * __ldg(k2 + pc + j));
-      o[j] = xv[j] > 0.f ? val : 0.f;
-    }
+    for (int j = 0; j < 8; ++j)
+      o[j] = xv[j] > 0.f ? fmaf(A[j], g[j], fmaf(Bc[j], xv[j], Cc[j])) : 0.f;
     st_stream16(gx + i * 8, pack8(o));
   }
 }
@@ -1147,18 +1190,30 @@ extern "C" int wu_adain_style_fwd(const float* cond, const float* lw, const floa
   return WU_OK;
 }
 extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u,
-                                    int B, int h, int w, int C, float p_drop, uint64_t seed,
-                                    const uint8_t* mask, int x_bcast, wu_stream_t stream) {
+                                    uint8_t* keep_bits, int B, int h, int w, int C, float p_drop,
+                                    uint64_t seed, const uint8_t* mask, int x_bcast,
+                                    wu_stream_t stream) {
   WU_REQUIRE(x && scale && shift && u && B > 0 && h > 0 && w > 0, "wu_adain_up_drop_fwd: bad args");
   WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_up_drop_fwd: C=%d must be a multiple of 8", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
+  WU_REQUIRE(p_drop == 0.f || keep_bits != nullptr,
+             "wu_adain_up_drop_fwd: keep_bits is required when p_drop > 0");
   const long long gy = (long long)B * ((2 * h + kRowsPerThread - 1) / kRowsPerThread);
   WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_fwd: B*ceil(2h/4)=%lld exceeds 65535", gy);
-  const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
   dim3 grid((unsigned)((2 * w * (C / 8) + 255) / 256), (unsigned)gy);
-  adain_up_drop_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, scale, shift, (bf16*)u, h, w, C, 1.f / (1.f - p_drop), thr, seed, mask,
-      x_bcast ? 0 : 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_keep = 1.f / (1.f - p_drop);
+  const int xm = x_bcast ? 0 : 1;
+  if (p_drop == 0.f)
+    adain_up_drop_fwd_kernel<kDropNone><<<grid, 256, 0, st>>>(
+        (const bf16*)x, scale, shift, (bf16*)u, nullptr, h, w, C, 1.f, 0u, seed, nullptr, xm);
+  else if (mask != nullptr)
+    adain_up_drop_fwd_kernel<kDropInjected><<<grid, 256, 0, st>>>(
+        (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep, 1u, seed, mask, xm);
+  else
+    adain_up_drop_fwd_kernel<kDropPhilox><<<grid, 256, 0, st>>>(
+        (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep,
+        dropout_threshold(p_drop), seed, nullptr, xm);
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
   return WU_OK;
 }
@@ -1168,21 +1223,23 @@ extern "C" size_t wu_adain_up_drop_bwd_scratch_bytes(int B, int h, int w, int C)
 }
 extern "C" int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean,
                                     const float* rstd, void* gz, float* partial, void* scratch,
-                                    int B, int h, int w, int C, float p_drop, uint64_t seed,
-                                    const uint8_t* mask, wu_stream_t stream) {
+                                    int B, int h, int w, int C, float p_drop,
+                                    const uint8_t* keep_bits, wu_stream_t stream) {
   WU_REQUIRE(gu && x && mean && rstd && gz && partial && scratch && B > 0 && h > 0 && w > 0,
              "wu_adain_up_drop_bwd: bad args");
   WU_REQUIRE_ADAIN_C("wu_adain_up_drop_bwd", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_bwd: p_drop=%f out of [0,1)", p_drop);
+  WU_REQUIRE(p_drop == 0.f || keep_bits != nullptr,
+             "wu_adain_up_drop_bwd: keep_bits (from the forward pass) is required when p_drop > 0");
   const long long gy = (long long)B * ((2 * h + kRowsPerThread - 1) / kRowsPerThread);
   WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_bwd: B*ceil(2h/4)=%lld exceeds 65535", gy);
   const int nchunk = wu_adain_stats_chunks(h * w);
   const int lanes = C / 8, groups = 256 / lanes;
-  const uint32_t thr = p_drop > 0.f ? (mask ? 1u : dropout_threshold(p_drop)) : 0u;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((w * (C / 8) + 255) / 256), (unsigned)gy);
-  adain_drop_hpass_kernel<<<grid, 256, 0, st>>>((const bf16*)gu, (bf16*)scratch, h, w, C,
-                                                1.f / (1.f - p_drop), thr, seed, mask);
+  adain_drop_hpass_kernel<<<grid, 256, 0, st>>>((const bf16*)gu, (bf16*)scratch,
+                                                p_drop > 0.f ? keep_bits : nullptr, h, w, C,
+                                                1.f / (1.f - p_drop));
   WU_CHECK_LAUNCH("adain_drop_hpass_kernel");
   adain_up_vpass_kernel<<<B * nchunk, 256, 2 * groups * C * sizeof(float), st>>>(
       (const bf16*)scratch, (const bf16*)x, mean, rstd, (bf16*)gz, partial, h, w, C, nchunk);
@@ -1190,15 +1247,18 @@ extern "C" int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* 
   return WU_OK;
 }
 extern "C" int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb,
-                                  const float* partial, const float* ystd, float* k1, float* k2,
-                                  float* gh, float* dlw, float* dlb, int B, int C, int nc, int HW,
+                                  const float* partial, const float* ystd, const float* mean,
+                                  const float* rstd, float* k1, float* k2, float* coef, float* gh,
+                                  float* dlw, float* dlb, int B, int C, int nc, int HW,
                                   wu_stream_t stream) {
-  WU_REQUIRE(cond && lw && lb && partial && ystd && k1 && k2 && gh && dlw && dlb,
+  WU_REQUIRE(cond && lw && lb && partial && ystd && mean && rstd && k1 && k2 && coef && gh && dlw &&
+                 dlb,
              "wu_adain_style_bwd: null pointer");
   WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0, "wu_adain_style_bwd: bad shape");
+  WU_REQUIRE((B * C) % 4 == 0, "wu_adain_style_bwd: B*C=%d must be a multiple of 4", B * C);
   cudaStream_t st = (cudaStream_t)stream;
-  adain_style_bwd_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(cond, lw, lb, partial, ystd, k1, k2,
-                                                              gh, B, C, nc, HW,
+  adain_style_bwd_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(cond, lw, lb, partial, ystd, mean, rstd,
+                                                              k1, k2, coef, gh, B, C, nc, HW,
                                                               wu_adain_stats_chunks(HW));
   WU_CHECK_LAUNCH("adain_style_bwd_kernel");
   adain_style_bwd_params_kernel<<<(4 * C + 127) / 128, 128, 0, st>>>(gh, cond, dlw, dlb, B, 4 * C, nc);
@@ -1215,16 +1275,13 @@ extern "C" int wu_adain_apply(const void* x, const float* scale, const float* sh
   WU_CHECK_LAUNCH("adain_apply_kernel");
   return WU_OK;
 }
-extern "C" int wu_adain_bwd_apply(const void* gz, const void* x, const float* mean,
-                                  const float* rstd, const float* ystd, const float* k1,
-                                  const float* k2, void* gx, int B, int HW, int C,
-                                  wu_stream_t stream) {
-  WU_REQUIRE(gz && x && mean && rstd && ystd && k1 && k2 && gx && B > 0 && HW > 0,
-             "wu_adain_bwd_apply: bad args");
+extern "C" int wu_adain_bwd_apply(const void* gz, const void* x, const float* coef, void* gx, int B,
+                                  int HW, int C, wu_stream_t stream) {
+  WU_REQUIRE(gz && x && coef && gx && B > 0 && HW > 0, "wu_adain_bwd_apply: bad args");
   WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_bwd_apply: C=%d must be a multiple of 8", C);
   const long long total = (long long)B * HW * (C / 8);
   adain_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)gz, (const bf16*)x, mean, rstd, ystd, k1, k2, (bf16*)gx, B, HW, C);
+      (const bf16*)gz, (const bf16*)x, coef, (bf16*)gx, B, HW, C);
   WU_CHECK_LAUNCH("adain_bwd_apply_kernel");
   return WU_OK;
 }
