@@ -263,6 +263,24 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
     extras = {}
+    if not args.no_extras and world == 1:
+        # NOT the headline: the same iteration with ONE generator forward shared by the D and the G
+        # update (train_step.GDTrainStep(share_fake=True)) — statistically equivalent to the
+        # reference's two forwards with independent dropout draws, not bitwise; reported for context
+        shared = GDTrainStep(G, D, lr=1e-4, share_fake=True)
+        for i in range(3):
+            shared.step(*resident[i % n_host])
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            shared.step(*resident[i % n_host])
+        e1.record()
+        barrier()
+        ms_sh = e0.elapsed_time(e1)
+        extras["shared_forward_variant"] = {
+            "value": B * args.steps / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh / args.steps,
+            "note": "1 G forward per iteration instead of the reference's 2 (different dropout "
+                    "sample for the D update): not the reference schedule, not the headline"}
     roof = None
     peak_burst, peak_sust, hbm, peak_src = peaks()
     if not args.no_extras:

@@ -120,8 +120,13 @@ class GDTrainStep:
     """
 
     def __init__(self, G, D, lr=1e-4, estimator=None, d_autocast=True, eps_con=1e-2, group=None,
-                 overlap=True, distributed=None):
+                 overlap=True, distributed=None, share_fake=False):
         self.G, self.D, self.estimator = G, D, estimator
+        # share_fake=True is NOT the reference's schedule: the reference runs the generator twice per
+        # iteration (t_cls_train.py:302 and :242) with two independent dropout draws; sharing one
+        # forward between the D and the G update is statistically equivalent but not bitwise
+        #  and saves one generator forward.  Default: faithful.
+        self.share_fake = share_fake
         self.d_autocast = d_autocast
         self.d_channels_last = next(D.parameters()).is_cuda
         if self.d_channels_last:  # cuDNN's bf16 tensor-core kernels are NHWC: avoid per-conv transposes
@@ -168,8 +173,12 @@ class GDTrainStep:
         # ---- discriminator update (t_cls_train.py:288-312)
         self._zero(self.d_opt, self.d_buckets)
         real = self._disc(images, c_real)
-        with torch.no_grad():  # the reference builds this graph and drops it with .detach() (:302-303)
-            fake_img = G(images, c_target, dropout_masks=masks_d)
+        if self.share_fake:
+            shared = G(images, c_target, dropout_masks=masks_g)  # one forward for both updates
+            fake_img = shared.detach()
+        else:
+            with torch.no_grad():  # the reference builds this graph and drops it with .detach() (:302-303)
+                fake_img = G(images, c_target, dropout_masks=masks_d)
         fake = self._disc(fake_img, c_target)
         d_loss = dis_hinge(fake, real)
         d_loss.backward()
@@ -182,7 +191,7 @@ class GDTrainStep:
         for p in d_params:  # D's weight gradients of this pass are discarded by the reference
             p.requires_grad_(False)
         try:
-            fake_img = G(images, c_target, dropout_masks=masks_g)
+            fake_img = shared if self.share_fake else G(images, c_target, dropout_masks=masks_g)
             fake = self._disc(fake_img, c_target)
             g_adv = gen_hinge(fake)
             g_l1 = l1_loss(fake_img, images)  # logged only (:255)
