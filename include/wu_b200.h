@@ -161,6 +161,15 @@ size_t wu_bias_act_bwd_workspace_bytes(int C);
 int wu_bias_act_bwd(const void* gy, const void* y, void* g, float* db, float slope, long long npix,
                     int C, void* workspace, size_t workspace_bytes, wu_stream_t stream);
 
+/* ---- multi-tensor Adam (t_cls_train.py:184-185) ---------------------------------
+ * torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, no amsgrad)
+ * for a whole parameter list in one launch.  `tensors`: device array of records
+ * {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64 numel} (40 bytes);
+ * `chunks`: device array of {int32 tensor; int32 count; int64 start} (16 bytes), one CTA each.
+ * `step` is the 1-based step count of this update. */
+int wu_adam_multi(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, wu_stream_t stream);
+
 /* ---- layout helpers (tests, interop with NCHW fp32 PyTorch tensors) ---------------------------*/
 int wu_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W,
                              wu_stream_t stream);

@@ -99,3 +99,37 @@ def test_loss_curve_against_reference_golden(cuda):
     err = np.abs(curve - ref) / np.maximum(np.abs(ref), 1.0)
     assert err[:, big].max() < 5e-2, err
     assert err[:3].max() < 1.5e-1, err
+
+
+def test_fused_adam_matches_torch(cuda):
+    """wu_adam_multi == torch.optim.Adam (the reference's optimiser settings) over several steps,
+    including a parameter that never receives a gradient and a channels_last parameter."""
+    from weather_unet_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(64, 3, 3, 3), (64,), (256, 768, 3, 3), (2048, 5), (5, 5), (100001,)]
+    ps_a = [torch.randn(s, device=cuda).requires_grad_(True) for s in shapes]
+    ps_a[0] = ps_a[0].detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ps_b = [p.detach().clone(memory_format=torch.preserve_format).requires_grad_(True) for p in ps_a]
+    lr = 1e-3
+    oa = FusedAdam(ps_a, lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
+    ob = torch.optim.Adam(ps_b, lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for it in range(4):
+        for i, (a, b) in enumerate(zip(ps_a, ps_b)):
+            if i == 4:
+                continue  # never gets a gradient (like adain*.emb.weight)
+            gr = torch.randn(shapes[i], generator=g).to(cuda)
+            a.grad = gr.clone().contiguous(memory_format=torch.channels_last) if i == 0 else gr.clone()
+            b.grad = a.grad.clone(memory_format=torch.preserve_format)
+        oa.step()
+        ob.step()
+    for a, b in zip(ps_a, ps_b):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), (a - b).abs().max()
+    assert torch.equal(ps_a[4], ps_b[4])
+    oa2 = FusedAdam(ps_a, lr=lr, betas=(0.5, 0.9), eps=1e-6, weight_decay=0.0)
+    ob2 = torch.optim.Adam(ps_b, lr=lr, betas=(0.5, 0.9), eps=1e-6, weight_decay=0.0)
+    for it in range(3):
+        oa2.step()
+        ob2.step()
+    for a, b in zip(ps_a, ps_b):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "wu_bias_act_fwd": (I, [P, P, F, c_longlong, I, P]),
     "wu_bias_act_bwd_workspace_bytes": (SZ, [I]),
     "wu_bias_act_bwd": (I, [P, P, P, P, F, c_longlong, I, P, SZ, P]),
+    "wu_adam_multi": (I, [P, P, I, F, F, F, F, F, I, P]),
     "wu_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
     "wu_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),
 }

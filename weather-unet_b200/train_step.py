@@ -120,7 +120,7 @@ class GDTrainStep:
     """
 
     def __init__(self, G, D, lr=1e-4, estimator=None, d_autocast=True, eps_con=1e-2, group=None,
-                 overlap=True, distributed=None, share_fake=False):
+                 overlap=True, distributed=None, share_fake=False, fused_adam=None):
         self.G, self.D, self.estimator = G, D, estimator
         # share_fake=True is NOT the reference's schedule: the reference runs the generator twice per
         # iteration (t_cls_train.py:302 and :242) with two independent dropout draws; sharing one
@@ -149,8 +149,14 @@ class GDTrainStep:
                 for t in list(m.parameters()) + list(m.buffers()):
                     dist.broadcast(t.data, src=0, group=group)
         # t_cls_train.py:184-185: Adam, betas (0, 0.999), L2 weight decay lr/20 (not AdamW)
-        self.g_opt = torch.optim.Adam(G.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
-        self.d_opt = torch.optim.Adam(D.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
+        if fused_adam is None:
+            fused_adam = next(G.parameters()).is_cuda
+        if fused_adam:  # same rule, one launch per model (optim.py / wu_adam_multi)
+            from .optim import FusedAdam as Adam
+        else:
+            Adam = torch.optim.Adam
+        self.g_opt = Adam(G.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
+        self.d_opt = Adam(D.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
 
     def _disc(self, x, c):
         if self.d_channels_last:
