@@ -40,8 +40,8 @@ class FusedAdam(torch.optim.Optimizer):
             for start in range(0, p.numel(), CHUNK):
                 crec += struct.pack("<iiq", ti, min(CHUNK, p.numel() - start), start)
                 n_chunks += 1
-        tens = torch.frombuffer(bytes(trec), dtype=torch.uint8).pin_memory().to(dev, non_blocking=True)
-        chk = torch.frombuffer(bytes(crec), dtype=torch.uint8).pin_memory().to(dev, non_blocking=True)
+        tens = torch.frombuffer(trec, dtype=torch.uint8).pin_memory().to(dev, non_blocking=True)
+        chk = torch.frombuffer(crec, dtype=torch.uint8).pin_memory().to(dev, non_blocking=True)
         cache.update(key=key, tensors=tens, chunks=chk, n=n_chunks)
         return tens, chk, n_chunks
 
@@ -57,13 +57,11 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             dev = items[0].device
             for p in items:
+                span = 1 + sum((n - 1) * st_ for n, st_ in zip(p.shape, p.stride()))
                 if not (p.is_cuda and p.dtype == torch.float32 and p.grad.dtype == torch.float32
-                        and p.is_contiguous(memory_format=torch.contiguous_format if p.dim() != 4 else
-                                            (torch.channels_last if not p.is_contiguous() else
-                                             torch.contiguous_format))
-                        and p.grad.stride() == p.stride()):
-                    raise RuntimeError("FusedAdam: fp32 CUDA parameters with dense gradients of the "
-                                       "same strides are required")
+                        and span == p.numel() and p.grad.stride() == p.stride()):
+                    raise RuntimeError("FusedAdam: fp32 CUDA parameters that are dense in memory, with "
+                                       "gradients of the same strides, are required")
                 st = self.state[p]
                 if not st:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
