@@ -362,9 +362,11 @@ struct ConvCfg2 {
   static constexpr int kABytes = kARows * 1024;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kSA = (T == 4) ? 2 : 3;
-  static constexpr int kSB = BN == 64 ? 6 : (BN == 128 ? 5 : 4);
+  static constexpr int kSB = BN == 64 ? 5 : (BN == 128 ? 4 : 3);
   static constexpr int kStagingBytes = 2 * 16384;
-  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + kStagingBytes + 1024 + 1024;
+  static constexpr int kMaskBytes = 16384;  // dgrad: ReLU-mask tile of the next chunk (cp.async)
+  static constexpr int kSmemBytes =
+      kSA * kABytes + kSB * kBBytes + kStagingBytes + kMaskBytes + 1024 + 1024;
   static constexpr uint32_t kTmemCols = 2 * T * BN;
   static_assert(kTmemCols == 512, "TMEM budget: 2 x T x BN must be 512 columns");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -386,7 +388,8 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + SA * Cfg::kABytes;
   const uint32_t staging_base = b_base + SB * Cfg::kBBytes;
-  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
+  const uint32_t mask_base = staging_base + Cfg::kStagingBytes;
+  const uint32_t bar_base = mask_base + Cfg::kMaskBytes;
   auto fullA = [&](int i) { return bar_base + 8u * i; };
   auto emptyA = [&](int i) { return bar_base + 8u * (SA + i); };
   auto fullB = [&](int i) { return bar_base + 8u * (2 * SA + i); };
@@ -522,23 +525,31 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int ph = row >> 3, pw = row & 7;
     constexpr int NCH = BN / 64;
     uint32_t store_count = 0;
-    // ReLU-gradient mask of the next (tile, t, chunk) is fetched one step ahead so that its L2
-    // latency hides behind the TMEM drain / staging of the current one
-    uint4 mk[8];
-    bool mk_ok = false;
-    auto fetch_mask = [&](int tile, int t, int chunk, uint4 (&m)[8]) -> bool {
-      if (p.mask == nullptr || tile >= p.num_tiles) return false;
+    // dgrad: the ReLU-gradient mask tile (128 px x 64 ch of the layer below) of the NEXT chunk is
+    // copied global -> shared with coalesced 16-byte cp.async while the current chunk is processed;
+    // each thread then reads its own pixel row from shared memory (XOR-swizzled, conflict free).
+    // (Per-thread row loads from global kept the LSU pipe ~90 % busy: 32 lines per request.)
+    const bool has_mask = p.mask != nullptr;
+    const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
+    auto issue_mask = [&](int tile, int t, int chunk) {
+      if (!has_mask || tile >= p.num_tiles) return;
       int b, h0, w0, n0;
       decode(tile, b, h0, w0, n0);
-      const int h = h0 + 16 * t + ph, w = w0 + pw;
-      if (h >= p.H || w >= p.W) return false;
-      const uint4* mp = reinterpret_cast<const uint4*>(
-          p.mask + ((size_t)(b * p.H + h) * p.W + w) * p.cout + n0 + chunk * 64);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = __ldg(mp + j);
-      return true;
+      for (int j = 0; j < 8; ++j) {
+        const int u = et + 128 * j;      // 16-byte unit of the [128 px][64 ch] tile
+        const int r = u >> 3, c = u & 7;  // pixel row of the tile, 8-channel chunk
+        const int h = h0 + 16 * t + (r >> 3), w = w0 + (r & 7);
+        const bool ok = (h < p.H) && (w < p.W);
+        const __nv_bfloat16* src =
+            p.mask + ((size_t)(b * p.H + (ok ? h : 0)) * p.W + (ok ? w : 0)) * p.cout + n0 +
+            chunk * 64 + c * 8;
+        cp_async16(mask_base + r * 128 + ((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
     };
-    mk_ok = fetch_mask(blockIdx.x, 0, 0, mk);
+    uint4 mk[8];
+    issue_mask(blockIdx.x, 0, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -550,11 +561,18 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int t = 0; t < T; ++t) {
 #pragma unroll 1
         for (int chunk = 0; chunk < NCH; ++chunk) {
-          uint4 nx[8];
-          bool nx_ok;
-          if (chunk + 1 < NCH) nx_ok = fetch_mask(tile, t, chunk + 1, nx);
-          else if (t + 1 < T) nx_ok = fetch_mask(tile, t + 1, 0, nx);
-          else nx_ok = fetch_mask(tile + gridDim.x, 0, 0, nx);
+          if (has_mask) {
+            cp_async_wait_all();
+            named_bar_sync(3, 128);  // every thread's copies have landed
+            const uint8_t* mrow = smem + (mask_base - base) + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              mk[j] = *reinterpret_cast<const uint4*>(mrow + ((j ^ (row & 7)) << 4));
+            named_bar_sync(4, 128);  // everyone has read: the buffer may be refilled
+            if (chunk + 1 < NCH) issue_mask(tile, t, chunk + 1);
+            else if (t + 1 < T) issue_mask(tile, t + 1, 0);
+            else issue_mask(tile + gridDim.x, 0, 0);
+          }
           uint32_t v0[32], v1[32];
           const uint32_t taddr =
               tmem_base + ((uint32_t)(q * 32) << 16) + buf * (T * BN) + t * BN + chunk * 64;
@@ -568,11 +586,8 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
           const int cbase = n0 + chunk * 64;
           const float* bptr = p.bias != nullptr ? p.bias + cbase : nullptr;
           uint32_t pk0[16], pk1[16];
-          epilogue_half_r(v0, bptr, p.relu, mk_ok, mk, pk0);
-          epilogue_half_r(v1, bptr ? bptr + 32 : nullptr, p.relu, mk_ok, mk + 4, pk1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) mk[j] = nx[j];
-          mk_ok = nx_ok;
+          epilogue_half_r(v0, bptr, p.relu, has_mask, mk, pk0);
+          epilogue_half_r(v1, bptr ? bptr + 32 : nullptr, p.relu, has_mask, mk + 4, pk1);
           const uint32_t sbuf = staging_base + (store_count & 1u) * 16384u;
           ++store_count;
           if (issuer) tma_store_wait_read<1>();
