@@ -161,6 +161,27 @@ size_t wu_bias_act_bwd_workspace_bytes(int C);
 int wu_bias_act_bwd(const void* gy, const void* y, void* g, float* db, float slope, long long npix,
                     int C, void* workspace, size_t workspace_bytes, wu_stream_t stream);
 
+/* ---- discriminator stem (disc.py:28, nets.py:26-33 with in_channels = 3) --------
+ *   x fp32 NCHW [B][3][H][W] -> h1 = Conv2d(3,3,3,padding=1)(x) fp32 NCHW (no activation)
+ *   -> c1 = LeakyReLU(Conv2d(3,64,3,padding=1,stride=2)(h1)) NHWC bf16 [B][H/2][W/2][64].
+ * Weights arrive already spectrally normalised (fp32, [cout][cin][3][3]).  K = 27: FMA / HBM bound. */
+int wu_conv3to3_fprop(const float* x, const float* w, const float* bias, float* y, int B, int H,
+                      int W, wu_stream_t stream);
+int wu_conv3to64_s2_fprop(const float* h1, const float* w, const float* bias, float slope, void* dst,
+                          int B, int Hin, int Win, wu_stream_t stream);
+/* g = gradient at the stride-2 convolution's output, already LeakyReLU-masked (wu_bias_act_bwd with
+ * NULL-equivalent bias handling is not needed: use slope masking of the caller), NHWC bf16. */
+size_t wu_conv3to64_s2_wgrad_workspace_bytes(int B, int Hin, int Win);
+int wu_conv3to64_s2_wgrad(const float* h1, const void* g, float* dw, float* db, int B, int Hin,
+                          int Win, void* workspace, size_t workspace_bytes, wu_stream_t stream);
+int wu_conv3to64_s2_dgrad(const void* g, const float* w, float* g_h1, int B, int Hin, int Win,
+                          wu_stream_t stream);
+/* Backward of the 3->3 convolution: g_x fp32 NCHW (may be NULL), dw [3][3][3][3], db [3] (may be NULL). */
+size_t wu_conv3to3_bprop_workspace_bytes(void);
+int wu_conv3to3_bprop(const float* g_h1, const float* x, const float* w, float* g_x, float* dw,
+                      float* db, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                      wu_stream_t stream);
+
 /* ---- multi-tensor Adam (t_cls_train.py:184-185) ---------------------------------
  * torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, no amsgrad)
  * for a whole parameter list in one launch.  `tensors`: device array of records

@@ -133,3 +133,34 @@ def test_fused_adam_matches_torch(cuda):
         ob2.step()
     for a, b in zip(ps_a, ps_b):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_disc_stem_kernels(cuda):
+    """wu_conv3to3_* / wu_conv3to64_s2_* (discriminator stem) against PyTorch fp32 convolutions."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 3, 32, 48
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(cuda)
+    w0 = (torch.randn(3, 3, 3, 3, generator=g) * 0.4).to(cuda)
+    b0 = (torch.randn(3, generator=g) * 0.1).to(cuda)
+    w1 = (torch.randn(64, 3, 3, 3, generator=g) * 0.3).to(cuda)
+    b1 = (torch.randn(64, generator=g) * 0.1).to(cuda)
+    gy = torch.randn(B, 64, H // 2, W // 2, generator=g).to(cuda)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w0, b0, w1, b1)]
+    ref = F.leaky_relu(F.conv2d(F.conv2d(leaves[0], leaves[1], leaves[2], padding=1), leaves[3], leaves[4],
+                                stride=2, padding=1), 0.2)
+    ref.backward(gy)
+    mine = [t.clone().requires_grad_(True) for t in (x, w0, b0, w1, b1)]
+    out = K.disc_stem(*mine, 0.2)
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 4e-3
+    out.backward(gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    # the reference's gradient mask follows its own fp32 sign; ours follows the bf16 output: equal
+    # except where the pre-activation is ~0, hence rel-L2 tolerances of 1e-2
+    for name, a, r in zip(("x", "w0", "b0", "w1", "b1"), mine, leaves):
+        e = ((a.grad - r.grad).norm() / r.grad.norm()).item()
+        assert e < 1.5e-2, f"{name}: {e}"
+    # no gradient requested for the image (real images, detached fakes): g_x is skipped
+    mine2 = [x.clone()] + [t.clone().requires_grad_(True) for t in (w0, b0, w1, b1)]
+    K.disc_stem(*mine2, 0.2).backward(gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    assert torch.allclose(mine2[1].grad, mine[1].grad) and torch.allclose(mine2[3].grad, mine[3].grad)

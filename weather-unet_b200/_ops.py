@@ -212,6 +212,73 @@ def bias_act(x, bias, slope):
     return _BiasAct.apply(x, bias.float() if bias.dtype != torch.float32 else bias, slope)
 
 
+class _DiscStem(torch.autograd.Function):
+    """Discriminator stem: x (B,3,H,W) fp32 NCHW -> Conv(3,3)+bias -> Conv(3,64,stride 2)+bias ->
+    LeakyReLU -> (B,64,H/2,W/2) bf16 channels_last.  Weights arrive spectrally normalised (the
+    spectral_norm hook's output), so autograd continues into weight_orig / sigma on the torch side."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1, slope):
+        B, _, H, W = x.shape
+        dev = x.device
+        x = x.contiguous().float()
+        w0c, w1c = w0.detach().contiguous().float(), w1.detach().contiguous().float()
+        h1 = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        call("wu_conv3to3_fprop", ptr(x), ptr(w0c), ptr(b0), ptr(h1), B, H, W, stream())
+        c1 = torch.empty((B, H // 2, W // 2, 64), dtype=BF16, device=dev)
+        call("wu_conv3to64_s2_fprop", ptr(h1), ptr(w1c), ptr(b1), float(slope), ptr(c1), B, H, W,
+             stream())
+        ctx.save_for_backward(x, h1, c1, w0c, w1c)
+        ctx.slope = float(slope)
+        return c1.permute(0, 3, 1, 2)  # NCHW-shaped view of NHWC memory == channels_last
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, h1, c1, w0c, w1c = ctx.saved_tensors
+        B, _, H, W = x.shape
+        dev = x.device
+        need_x, need_w0, need_b0, need_w1, need_b1 = ctx.needs_input_grad[:5]
+        gy = gy.permute(0, 2, 3, 1)  # back to NHWC
+        if gy.dtype != BF16 or not gy.is_contiguous():
+            gy = gy.to(BF16).contiguous()
+        npix = B * (H // 2) * (W // 2)
+        g = torch.empty_like(gy)
+        db1 = torch.empty((64,), dtype=torch.float32, device=dev)
+        nb = query("wu_bias_act_bwd_workspace_bytes", 64)
+        ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+        call("wu_bias_act_bwd", ptr(gy), ptr(c1), ptr(g), ptr(db1), ctx.slope, npix, 64, ptr(ws), nb,
+             stream())
+        dw1 = None
+        if need_w1:
+            nb = query("wu_conv3to64_s2_wgrad_workspace_bytes", B, H, W)
+            ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+            dw1 = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=dev)
+            call("wu_conv3to64_s2_wgrad", ptr(h1), ptr(g), ptr(dw1), None, B, H, W, ptr(ws), nb,
+                 stream())
+        gx = dw0 = db0 = None
+        if need_x or need_w0 or need_b0:
+            gh = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+            call("wu_conv3to64_s2_dgrad", ptr(g), ptr(w1c), ptr(gh), B, H, W, stream())
+            nb = query("wu_conv3to3_bprop_workspace_bytes")
+            ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+            gx = torch.empty_like(x) if need_x else None
+            dw0 = torch.empty((3, 3, 3, 3), dtype=torch.float32, device=dev)
+            db0 = torch.empty((3,), dtype=torch.float32, device=dev)
+            call("wu_conv3to3_bprop", ptr(gh), ptr(x), ptr(w0c), ptr(gx), ptr(dw0), ptr(db0), B, H, W,
+                 ptr(ws), nb, stream())
+        return (gx, dw0 if need_w0 else None, db0 if need_b0 else None, dw1,
+                db1 if need_b1 else None, None)
+
+
+def disc_stem_supported(x):
+    return (x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 2 == 0
+            and x.shape[3] % 8 == 0 and x.dtype == torch.float32)
+
+
+def disc_stem(x, w0, b0, w1, b1, slope):
+    return _DiscStem.apply(x, w0, b0, w1, b1, slope)
+
+
 def nchw_to_nhwc(x):
     """fp32 NCHW -> bf16 NHWC."""
     B, C, H, W = x.shape

@@ -176,12 +176,16 @@ conv_first_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w
   }
 }
 
-// Register-tiled variant for W % 4 == 0: thread = 4 consecutive pixels of a row x 8 channels
-// (32 accumulators, 54 inputs in registers), 8 threads cover the 64 channels of a pixel quad.
+// Register-tiled variant for W % 4 == 0: thread = 4 consecutive output pixels of a row x 8 channels
+// (32 accumulators, inputs in registers), 8 threads cover the 64 channels of a pixel quad.
+// STRIDE 1: the generator's first layer (ReLU = slope 0).  STRIDE 2: the discriminator stem's
+// Conv2d(3, 64, 3, padding=1, stride=2) + LeakyReLU (nets.py:30-32); H, W are OUTPUT sizes.
+template <int STRIDE>
 __global__ void __launch_bounds__(256)
 conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int B,
-                           int H, int W) {
+                           int H, int W, float slope) {
+  constexpr int NC = 3 * STRIDE + 3;  // input columns feeding 4 adjacent outputs
   __shared__ __align__(16) float ws[27][64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
@@ -190,6 +194,7 @@ conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict_
   }
   if (threadIdx.x < 64) bs[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.f;
   __syncthreads();
+  const int Hin = H * STRIDE, Win = W * STRIDE;
   const int Wq = W >> 2;
   const long long nquad = (long long)B * H * Wq;
   const int cg = threadIdx.x & 7;
@@ -199,18 +204,18 @@ conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict_
     const long long t = qd / Wq;
     const int hq = (int)(t % H);
     const int b = (int)(t / H);
-    float in[3][3][6];
+    float in[3][3][NC];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const int hh = hq + r - 1;
-        const float* row = x + (((long long)b * 3 + ci) * H + hh) * W;
-        const bool hv = hh >= 0 && hh < H;
+        const int hh = hq * STRIDE + r - 1;
+        const float* row = x + (((long long)b * 3 + ci) * Hin + hh) * Win;
+        const bool hv = hh >= 0 && hh < Hin;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const int ww = wq + c - 1;
-          in[ci][r][c] = (hv && ww >= 0 && ww < W) ? __ldg(row + ww) : 0.f;
+        for (int c = 0; c < NC; ++c) {
+          const int ww = wq * STRIDE + c - 1;
+          in[ci][r][c] = (hv && ww >= 0 && ww < Win) ? __ldg(row + ww) : 0.f;
         }
       }
     float acc[4][8];
@@ -229,7 +234,7 @@ conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict_
           const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            const float xv = in[ci][r][p + s3];
+            const float xv = in[ci][r][p * STRIDE + s3];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xv, wv[j], acc[p][j]);
           }
@@ -239,7 +244,7 @@ conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict_
     for (int p = 0; p < 4; ++p) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(acc[p][j], 0.f);
+      for (int j = 0; j < 8; ++j) o[j] = acc[p][j] > 0.f ? acc[p][j] : acc[p][j] * slope;
       *reinterpret_cast<uint4*>(dst + (px0 + p) * 64 + cg * 8) = pack8(o);
     }
   }
@@ -249,10 +254,13 @@ conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict_
 // Block: 256 threads = 4 pixel slices x (16 channel quads x 4 tap octets); 32 accumulators/thread.
 // Tiles of 64 pixels are double-buffered: the next tile's global loads are in flight (registers)
 // while the current tile is multiplied out of shared memory.
+// STRIDE 2: the discriminator stem's Conv2d(3, 64, 3, padding=1, stride=2); H, W = OUTPUT sizes.
 constexpr int kFirstWgradTile = 64;  // pixels staged per iteration
+template <int STRIDE>
 __global__ void __launch_bounds__(256)
 conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                         float* __restrict__ partial, int B, int H, int W) {
+  const int Hin = H * STRIDE, Win = W * STRIDE;
   __shared__ __align__(16) __nv_bfloat16 sdy[2][kFirstWgradTile][64];
   __shared__ __align__(16) float sp[2][kFirstWgradTile][32];
   __shared__ __align__(16) float red[4096];
@@ -287,13 +295,14 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
         const long long t = px / W;
         const int hq = (int)(t % H);
         const int b = (int)(t / H);
-        const float* plane = x + ((long long)b * 3 + sp_part) * H * W;
+        const float* plane = x + ((long long)b * 3 + sp_part) * Hin * Win;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const int hh = hq + r - 1, ww = wq + c - 1;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) rp[r * 3 + c] = __ldg(plane + (long long)hh * W + ww);
+            const int hh = hq * STRIDE + r - 1, ww = wq * STRIDE + c - 1;
+            if (hh >= 0 && hh < Hin && ww >= 0 && ww < Win)
+              rp[r * 3 + c] = __ldg(plane + (long long)hh * Win + ww);
           }
       } else {
         rp[0] = 1.f;  // slot 27: bias gradient
@@ -1069,8 +1078,8 @@ extern "C" int wu_conv_first_fprop(const float* x, const float* w, const float* 
   WU_REQUIRE(x && w && dst && B > 0 && H > 0 && W > 0, "wu_conv_first_fprop: bad args");
   const long long npix = (long long)B * H * W;
   if (W % 4 == 0) {
-    conv_first_fprop_x4_kernel<<<grid_for(npix / 4, 32, 16), 256, 0, (cudaStream_t)stream>>>(
-        x, w, bias, (bf16*)dst, B, H, W);
+    conv_first_fprop_x4_kernel<1><<<grid_for(npix / 4, 32, 16), 256, 0, (cudaStream_t)stream>>>(
+        x, w, bias, (bf16*)dst, B, H, W, 0.f);
     WU_CHECK_LAUNCH("conv_first_fprop_x4_kernel");
     return WU_OK;
   }
@@ -1097,7 +1106,7 @@ extern "C" int wu_conv_first_wgrad(const float* x, const void* dy, float* dw, fl
   WU_REQUIRE(workspace_bytes >= (size_t)blocks * 2048 * sizeof(float),
              "wu_conv_first_wgrad: workspace %zu too small", workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  conv_first_wgrad_kernel<<<blocks, 256, 0, st>>>(x, (const bf16*)dy, (float*)workspace, B, H, W);
+  conv_first_wgrad_kernel<1><<<blocks, 256, 0, st>>>(x, (const bf16*)dy, (float*)workspace, B, H, W);
   WU_CHECK_LAUNCH("conv_first_wgrad_kernel");
   conv_first_wgrad_final_kernel<<<8, 256, 0, st>>>((const float*)workspace, dw, db, blocks);
   WU_CHECK_LAUNCH("conv_first_wgrad_final_kernel");
@@ -1283,5 +1292,40 @@ extern "C" int wu_adain_bwd_apply(const void* gz, const void* x, const float* co
   adain_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)gz, (const bf16*)x, coef, (bf16*)gx, B, HW, C);
   WU_CHECK_LAUNCH("adain_bwd_apply_kernel");
+  return WU_OK;
+}
+
+// ---- discriminator stem, second convolution: Conv2d(3, 64, 3, padding=1, stride=2) + LeakyReLU
+extern "C" int wu_conv3to64_s2_fprop(const float* h1, const float* w, const float* bias, float slope,
+                                     void* dst, int B, int Hin, int Win, wu_stream_t stream) {
+  WU_REQUIRE(h1 && w && dst && B > 0 && Hin > 0 && Win > 0, "wu_conv3to64_s2_fprop: bad args");
+  WU_REQUIRE(Hin % 2 == 0 && Win % 8 == 0,
+             "wu_conv3to64_s2_fprop: need even Hin and Win %% 8 == 0 (got %d x %d)", Hin, Win);
+  const int H = Hin / 2, W = Win / 2;
+  const long long npix = (long long)B * H * W;
+  conv_first_fprop_x4_kernel<2><<<grid_for(npix / 4, 32, 16), 256, 0, (cudaStream_t)stream>>>(
+      h1, w, bias, (bf16*)dst, B, H, W, slope);
+  WU_CHECK_LAUNCH("conv_first_fprop_x4_kernel<2>");
+  return WU_OK;
+}
+extern "C" size_t wu_conv3to64_s2_wgrad_workspace_bytes(int B, int Hin, int Win) {
+  if (B <= 0 || Hin <= 0 || Win <= 0) return 0;
+  return (size_t)first_wgrad_blocks((long long)B * (Hin / 2) * (Win / 2)) * 2048 * sizeof(float);
+}
+extern "C" int wu_conv3to64_s2_wgrad(const float* h1, const void* g, float* dw, float* db, int B,
+                                     int Hin, int Win, void* workspace, size_t workspace_bytes,
+                                     wu_stream_t stream) {
+  WU_REQUIRE(h1 && g && dw && workspace && B > 0 && Hin > 0 && Win > 0,
+             "wu_conv3to64_s2_wgrad: bad args");
+  WU_REQUIRE(Hin % 2 == 0 && Win % 2 == 0, "wu_conv3to64_s2_wgrad: need even Hin, Win");
+  const int H = Hin / 2, W = Win / 2;
+  const int blocks = first_wgrad_blocks((long long)B * H * W);
+  WU_REQUIRE(workspace_bytes >= (size_t)blocks * 2048 * sizeof(float),
+             "wu_conv3to64_s2_wgrad: workspace %zu too small", workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv_first_wgrad_kernel<2><<<blocks, 256, 0, st>>>(h1, (const bf16*)g, (float*)workspace, B, H, W);
+  WU_CHECK_LAUNCH("conv_first_wgrad_kernel<2>");
+  conv_first_wgrad_final_kernel<<<8, 256, 0, st>>>((const float*)workspace, dw, db, blocks);
+  WU_CHECK_LAUNCH("conv_first_wgrad_final_kernel");
   return WU_OK;
 }

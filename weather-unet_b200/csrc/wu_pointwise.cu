@@ -94,6 +94,187 @@ bias_act_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// discriminator stem (disc.py:28 / nets.py:26-33 with in_channels = 3):
+//   x (B,3,H,W) fp32 NCHW -> h1 = Conv2d(3,3,3,padding=1)(x)  (fp32 NCHW, no activation)
+//   -> c1 = LeakyReLU(Conv2d(3,64,3,padding=1,stride=2)(h1))   (NHWC bf16, wu_conv3to64_s2_*)
+// Three-channel tensors are FMA / HBM work, not tensor-core work (K = 27).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv3to3_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W) {
+  __shared__ float ws[81];
+  __shared__ float bs[3];
+  if (threadIdx.x < 81) ws[threadIdx.x] = w[threadIdx.x];
+  if (threadIdx.x < 3) bs[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const long long HW = (long long)H * W, npix = (long long)B * HW;
+  for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
+       px += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(px % W);
+    const long long t = px / W;
+    const int hq = (int)(t % H);
+    const long long b = t / H;
+    float acc[3] = {bs[0], bs[1], bs[2]};
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+          const int hh = hq + r - 1, ww = wq + s3 - 1;
+          const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                              ? __ldg(x + (b * 3 + ci) * HW + (long long)hh * W + ww)
+                              : 0.f;
+#pragma unroll
+          for (int co = 0; co < 3; ++co) acc[co] = fmaf(v, ws[co * 27 + ci * 9 + r * 3 + s3], acc[co]);
+        }
+#pragma unroll
+    for (int co = 0; co < 3; ++co) y[(b * 3 + co) * HW + (long long)hq * W + wq] = acc[co];
+  }
+}
+
+// Data gradient of the stride-2 convolution: g NHWC bf16 [B][H/2][W/2][64] -> g_h1 fp32 NCHW
+// [B][3][H][W].  8 lanes share a pixel (8 output channels of g each); only the taps whose parity
+// matches contribute: r = (y+1) % 2 (+2), Y = (y+1-r)/2, same for columns.
+__global__ void __launch_bounds__(256)
+conv3to64_s2_dgrad_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ w,
+                          float* __restrict__ gh, int B, int H, int W) {
+  __shared__ float ws[27][64];  // [ci*9 + r*3 + s][co]
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+    const int co = i / 27, k = i - co * 27;
+    ws[k][co] = w[i];
+  }
+  __syncthreads();
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long HW = (long long)H * W, npix = (long long)B * HW;
+  const int sub = threadIdx.x & 7;
+  const long long ngroups = (long long)gridDim.x * (blockDim.x >> 3);
+  for (long long px = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+       px < ((npix + 3) / 4) * 4; px += ngroups) {  // warp-uniform trip count (shuffles below)
+    const bool valid = px < npix;
+    const long long pxc = valid ? px : npix - 1;
+    const int xq = (int)(pxc % W);
+    const long long t = pxc / W;
+    const int yq = (int)(t % H);
+    const long long b = t / H;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int r = (yq + 1) & 1; r < 3; r += 2) {
+      const int Y = (yq + 1 - r) >> 1;
+      if (Y < 0 || Y >= Ho) continue;
+      for (int s3 = (xq + 1) & 1; s3 < 3; s3 += 2) {
+        const int X = (xq + 1 - s3) >> 1;
+        if (X < 0 || X >= Wo) continue;
+        float f[8];
+        unpack8p(__ldg(reinterpret_cast<const uint4*>(g + ((b * Ho + Y) * Wo + X) * 64 + sub * 8)), f);
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float* wr = &ws[ci * 9 + r * 3 + s3][sub * 8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[ci] = fmaf(f[e], wr[e], acc[ci]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], m);
+      acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], m);
+      acc[2] += __shfl_xor_sync(0xffffffffu, acc[2], m);
+    }
+    if (valid && sub < 3) gh[(b * 3 + sub) * HW + (long long)yq * W + xq] = acc[sub];
+  }
+}
+
+// Backward of Conv2d(3,3,3,padding=1): g_x = conv_transpose(g_h1, w0) (optional), and per-block
+// partial sums of dw0[co][ci][r][s] = sum g_h1[co] * x[ci][shifted], db0[co] = sum g_h1[co].
+constexpr int kStemBwdBlocks = 148 * 2;
+__global__ void __launch_bounds__(256)
+conv3to3_bprop_kernel(const float* __restrict__ gh, const float* __restrict__ x,
+                      const float* __restrict__ w, float* __restrict__ gx,
+                      float* __restrict__ partial, int B, int H, int W) {
+  __shared__ float ws[81];
+  __shared__ float red[8][84];
+  if (threadIdx.x < 81) ws[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const long long HW = (long long)H * W, npix = (long long)B * HW;
+  float dw[81];
+  float db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 81; ++i) dw[i] = 0.f;
+  for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
+       px += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(px % W);
+    const long long t = px / W;
+    const int hq = (int)(t % H);
+    const long long b = t / H;
+    const long long off = (long long)hq * W + wq;
+    const float g0 = gh[(b * 3 + 0) * HW + off], g1 = gh[(b * 3 + 1) * HW + off],
+                g2 = gh[(b * 3 + 2) * HW + off];
+    db[0] += g0; db[1] += g1; db[2] += g2;
+    float gxa[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s3 = 0; s3 < 3; ++s3) {
+        // weight gradient: x at (h+r-1, w+s-1)
+        const int hh = hq + r - 1, ww = wq + s3 - 1;
+        const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float xv = in ? __ldg(x + (b * 3 + ci) * HW + (long long)hh * W + ww) : 0.f;
+          dw[0 * 27 + ci * 9 + r * 3 + s3] = fmaf(g0, xv, dw[0 * 27 + ci * 9 + r * 3 + s3]);
+          dw[1 * 27 + ci * 9 + r * 3 + s3] = fmaf(g1, xv, dw[1 * 27 + ci * 9 + r * 3 + s3]);
+          dw[2 * 27 + ci * 9 + r * 3 + s3] = fmaf(g2, xv, dw[2 * 27 + ci * 9 + r * 3 + s3]);
+        }
+        // data gradient: g_h1 at (h+1-r, w+1-s)
+        if (gx != nullptr) {
+          const int h2 = hq + 1 - r, w2 = wq + 1 - s3;
+          if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) {
+            const long long o2 = (long long)h2 * W + w2;
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+              const float gv = __ldg(gh + (b * 3 + co) * HW + o2);
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci)
+                gxa[ci] = fmaf(gv, ws[co * 27 + ci * 9 + r * 3 + s3], gxa[ci]);
+            }
+          }
+        }
+      }
+    if (gx != nullptr) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) gx[(b * 3 + ci) * HW + off] = gxa[ci];
+    }
+  }
+  // block reduction of the 84 partial sums: warp shuffles, then 8 warps through shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 84; ++i) {
+    float v = i < 81 ? dw[i] : db[i - 81];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 84) {
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sum += red[wv][threadIdx.x];
+    partial[(size_t)blockIdx.x * 84 + threadIdx.x] = sum;
+  }
+}
+__global__ void conv3to3_bprop_final_kernel(const float* __restrict__ partial,
+                                            float* __restrict__ dw, float* __restrict__ db,
+                                            int nblocks) {
+  const int i = threadIdx.x;
+  if (i >= 84) return;
+  float sum = 0.f;
+  for (int b = 0; b < nblocks; ++b) sum += partial[(size_t)b * 84 + i];
+  if (i < 81) dw[i] = sum;
+  else if (db != nullptr) db[i - 81] = sum;
+}
+
 constexpr int kBiasActBlocks = 148 * 4;
 
 }  // namespace wu
@@ -134,5 +315,46 @@ extern "C" int wu_bias_act_bwd(const void* gy, const void* y, void* g, float* db
   bias_act_bwd_final_kernel<<<(C + 31) / 32, 256, 0, st>>>((const float*)workspace, db,
                                                            kBiasActBlocks, C);
   WU_CHECK_LAUNCH("bias_act_bwd_final_kernel");
+  return WU_OK;
+}
+
+// ---- discriminator stem entry points
+extern "C" int wu_conv3to3_fprop(const float* x, const float* w, const float* bias, float* y, int B,
+                                 int H, int W, wu_stream_t stream) {
+  WU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "wu_conv3to3_fprop: bad args");
+  const long long npix = (long long)B * H * W;
+  long long g = (npix + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  conv3to3_fprop_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W);
+  WU_CHECK_LAUNCH("conv3to3_fprop_kernel");
+  return WU_OK;
+}
+extern "C" int wu_conv3to64_s2_dgrad(const void* g, const float* w, float* g_h1, int B, int Hin,
+                                     int Win, wu_stream_t stream) {
+  WU_REQUIRE(g && w && g_h1 && B > 0 && Hin > 0 && Win > 0, "wu_conv3to64_s2_dgrad: bad args");
+  WU_REQUIRE(Hin % 2 == 0 && Win % 2 == 0, "wu_conv3to64_s2_dgrad: need even Hin, Win");
+  const long long npix = (long long)B * Hin * Win;
+  long long grid = (npix + 31) / 32;
+  if (grid > 148LL * 16) grid = 148LL * 16;
+  conv3to64_s2_dgrad_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g, w, g_h1, B, Hin, Win);
+  WU_CHECK_LAUNCH("conv3to64_s2_dgrad_kernel");
+  return WU_OK;
+}
+extern "C" size_t wu_conv3to3_bprop_workspace_bytes(void) {
+  return (size_t)kStemBwdBlocks * 84 * sizeof(float);
+}
+extern "C" int wu_conv3to3_bprop(const float* g_h1, const float* x, const float* w, float* g_x,
+                                 float* dw, float* db, int B, int H, int W, void* workspace,
+                                 size_t workspace_bytes, wu_stream_t stream) {
+  WU_REQUIRE(g_h1 && x && w && dw && workspace && B > 0 && H > 0 && W > 0,
+             "wu_conv3to3_bprop: bad args");
+  WU_REQUIRE(workspace_bytes >= wu_conv3to3_bprop_workspace_bytes(),
+             "wu_conv3to3_bprop: workspace %zu too small", workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv3to3_bprop_kernel<<<kStemBwdBlocks, 256, 0, st>>>(g_h1, x, w, g_x, (float*)workspace, B, H, W);
+  WU_CHECK_LAUNCH("conv3to3_bprop_kernel");
+  conv3to3_bprop_final_kernel<<<1, 96, 0, st>>>((const float*)workspace, dw, db, kStemBwdBlocks);
+  WU_CHECK_LAUNCH("conv3to3_bprop_final_kernel");
   return WU_OK;
 }

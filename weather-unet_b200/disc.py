@@ -47,10 +47,34 @@ class SNDisc(nn.Module):
         out = out + conv.bias.to(out.dtype).view(1, -1, 1, 1)
         return out if slope == 1.0 else F.leaky_relu(out, slope)
 
+    def _stem(self, x):
+        """conv1 block on the sm_100a stem kernels (3-channel FMA/HBM-bound work) when the input is
+        an fp32 CUDA image and bf16 autocast is on; None otherwise."""
+        try:
+            from . import _ops as K
+        except ImportError:
+            from weather_unet_b200 import _ops as K
+        if not (K.disc_stem_supported(x) and torch.is_autocast_enabled()
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+            return None
+        c0, c1, act = self.conv1[0], self.conv1[1], self.conv1[2]
+        for conv in (c0, c1):
+            for hook in conv._forward_pre_hooks.values():  # spectral norm of both weights
+                hook(conv, (x,))
+        with torch.autocast("cuda", enabled=False):
+            return K.disc_stem(x, c0.weight.float(), c0.bias.float(), c1.weight.float(),
+                               c1.bias.float(), act.negative_slope)
+
     def forward(self, x, c=None):
         feats = []
-        h = x
-        for i in range(1, 5):
+        h = self._stem(x)
+        first = 1
+        if h is not None:
+            feats.append(h)
+            first = 2
+        else:
+            h = x
+        for i in range(first, 5):
             blk = getattr(self, f"conv{i}")
             h = self._sn_conv(blk[0], h, 1.0)                       # no activation in between
             h = self._sn_conv(blk[1], h, blk[2].negative_slope)     # (nets.py:26-33)

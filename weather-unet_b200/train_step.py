@@ -159,8 +159,8 @@ class GDTrainStep:
         self.d_opt = Adam(D.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
 
     def _disc(self, x, c):
-        if self.d_channels_last:
-            x = x.contiguous(memory_format=torch.channels_last)
+        if self.d_channels_last and not (self.d_autocast and x.dtype == torch.float32):
+            x = x.contiguous(memory_format=torch.channels_last)  # (the stem kernels take NCHW fp32)
         if self.d_autocast and x.is_cuda:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return self.D(x, c)[0].float()
