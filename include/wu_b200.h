@@ -182,6 +182,28 @@ int wu_conv3to3_bprop(const float* g_h1, const float* x, const float* w, float* 
                       float* db, int B, int H, int W, void* workspace, size_t workspace_bytes,
                       wu_stream_t stream);
 
+/* ---- discriminator trunk: 3x3 / stride 2 / pad 1 convolution on tcgen05 ----------
+ * Replaces spectral_norm(nn.Conv2d(cin, cout, 3, padding=1, stride=2)) + nn.LeakyReLU(0.2)
+ * (nets.py:26-33, disc.py:12-15,28-31) and its autograd.  The stride-1 convolution in front of it
+ * (nets.py:28-29, no activation) is wu_conv3x3_fprop with relu = 0.  Weights arrive spectrally
+ * normalised and packed by wu_pack_conv3x3_weights.  src NHWC bf16 [B][Hin][Win][cin];
+ * dst / dy NHWC bf16 [B][Ho][Wo][cout], Ho = ceil(Hin/2), Wo = ceil(Win/2).
+ *   fprop: dst = lrelu(bias + conv_s2(src, w_packed), slope)   (slope 1 = no activation)
+ *   dgrad: dx[b,yi,xi,ci] = sum_{r,s,co : yi+1-r, xi+1-s even} dy[b,(yi+1-r)/2,(xi+1-s)/2,co] * w[co][ci][r][s]
+ *          (w_dgrad from wu_pack_conv3x3_weights; dy already LeakyReLU-masked: wu_bias_act_bwd)
+ *   wgrad: dw[co][ci][r][s] = sum_{b,yo,xo} dy[b,yo,xo,co] * src[b,2yo+r-1,2xo+s-1,ci]; db optional.
+ * cin, cout multiples of 64; the N dimension (cout for fprop / wgrad, cin for dgrad) must be 64, 128
+ * or a multiple of 256. */
+int wu_conv3x3_s2_fprop(const void* src, int cin, const void* w_packed, const float* bias,
+                        float slope, void* dst, int cout, int B, int Hin, int Win,
+                        wu_stream_t stream);
+int wu_conv3x3_s2_dgrad(const void* dy, int cout, const void* w_dgrad, void* dx, int cin, int B,
+                        int Hin, int Win, wu_stream_t stream);
+size_t wu_conv3x3_s2_wgrad_workspace_bytes(int cin, int cout, int B, int Hin, int Win);
+int wu_conv3x3_s2_wgrad(const void* src, int cin, const void* dy, int cout, int B, int Hin, int Win,
+                        float* dw, float* db, void* workspace, size_t workspace_bytes,
+                        wu_stream_t stream);
+
 /* ---- multi-tensor Adam (t_cls_train.py:184-185) ---------------------------------
  * torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, no amsgrad)
  * for a whole parameter list in one launch.  `tensors`: device array of records

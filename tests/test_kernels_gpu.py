@@ -99,6 +99,78 @@ def test_conv3x3_wgrad(cuda, B, H, W, c0, c1, cout):
     assert torch.equal(dw, dw2), "wgrad must be deterministic"
 
 
+S2_CASES = [
+    # B, H, W, cin, cout   (discriminator trunk shapes, scaled down, plus ragged / odd sizes)
+    (2, 32, 32, 64, 128),
+    (2, 16, 16, 128, 256),
+    (3, 8, 8, 256, 512),
+    (1, 24, 40, 64, 64),
+    (2, 18, 30, 128, 128),
+    (1, 17, 23, 64, 128),
+    (4, 64, 64, 64, 128),
+]
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", S2_CASES)
+def test_conv3x3_s2(cuda, B, H, W, cin, cout):
+    """Stride-2 convolution (nets.py:30-31 + LeakyReLU :32): forward, data gradient, weight and
+    bias gradient against PyTorch fp32 on bf16-representable inputs."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(7 * B + H + cin + cout)
+    x = bf(torch.randn(B, cin, H, W, generator=g)).to(cuda)
+    w = bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(cuda)
+    b = torch.randn(cout, generator=g).to(cuda)
+    wf, wd = K.pack_conv3x3_weights(w)
+    y = K.conv3x3_s2(nhwc(x), wf, b, 0.2, cout)
+    ref = F.leaky_relu(F.conv2d(x, w, b, stride=2, padding=1), 0.2)
+    assert nchw(y).shape == ref.shape
+    assert rel(nchw(y), ref) < 6e-3
+    y1 = K.conv3x3_s2(nhwc(x), wf, None, 1.0, cout)  # no bias, no activation
+    ref1 = F.conv2d(x, w, None, stride=2, padding=1)
+    assert rel(nchw(y1), ref1) < 6e-3
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    dy = bf(torch.randn(B, cout, Ho, Wo, generator=g)).to(cuda)
+    dx = K.conv3x3_s2_dgrad(nhwc(dy), wd, cin, H, W)
+    ref_dx = torch.nn.grad.conv2d_input((B, cin, H, W), w, dy, stride=2, padding=1)
+    assert rel(nchw(dx), ref_dx) < 6e-3
+    dw, db = K.conv3x3_s2_wgrad(nhwc(x), nhwc(dy))
+    ref_w = torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), dy, stride=2, padding=1)
+    assert rel(dw, ref_w) < 2e-3
+    assert rel(db, dy.sum(dim=(0, 2, 3))) < 1e-4
+    dw2, _ = K.conv3x3_s2_wgrad(nhwc(x), nhwc(dy), want_bias=False)
+    assert torch.equal(dw, dw2), "wgrad must be deterministic"
+
+
+def test_disc_block(cuda):
+    """One discriminator block (nets.py:26-33) through _DiscBlock against PyTorch fp32 autograd."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, H, W, cin, cout = 2, 32, 32, 64, 128
+    x = bf(torch.randn(B, cin, H, W, generator=g)).to(cuda)
+    w0 = bf(torch.randn(cin, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(cuda)
+    b0 = (torch.randn(cin, generator=g) * 0.1).to(cuda)
+    w1 = bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(cuda)
+    b1 = (torch.randn(cout, generator=g) * 0.1).to(cuda)
+    gy = bf(torch.randn(B, cout, H // 2, W // 2, generator=g)).to(cuda)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w0, b0, w1, b1)]
+    # the block stores its intermediate activation in bf16; the fp32 reference rounds at the same
+    # point (straight-through), otherwise ~0.1 % of the LeakyReLU masks differ (pre-activations
+    # within the rounding error of zero) and the gradients differ by 3e-2 rel-L2 for that reason alone
+    h_ref = F.conv2d(leaves[0], leaves[1], leaves[2], padding=1)
+    h_ref = h_ref + (bf(h_ref) - h_ref).detach()
+    ref = F.leaky_relu(F.conv2d(h_ref, leaves[3], leaves[4], stride=2, padding=1), 0.2)
+    ref.backward(gy)
+    mine = [t.clone().requires_grad_(True) for t in (w0, b0, w1, b1)]
+    xin = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = K.disc_block(xin, *mine, 0.2)
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert rel(out, ref) < 8e-3
+    out.backward(gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    # the gradient of the intermediate activation is stored in bf16 as well: 1e-2 rel-L2
+    errs = {name: rel(a.grad, r.grad) for name, a, r in zip(("x", "w0", "b0", "w1", "b1"), [xin] + mine, leaves)}
+    assert max(errs.values()) < 1e-2, errs
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 24, 40), (3, 64, 64)])
 def test_conv_first(cuda, B, H, W):
     from weather_unet_b200 import _ops as K

@@ -53,6 +53,10 @@ SIGNATURES = {
     "wu_conv3to64_s2_dgrad": (I, [P, P, P, I, I, I, P]),
     "wu_conv3to3_bprop_workspace_bytes": (SZ, []),
     "wu_conv3to3_bprop": (I, [P, P, P, P, P, P, I, I, I, P, SZ, P]),
+    "wu_conv3x3_s2_fprop": (I, [P, I, P, P, F, P, I, I, I, I, P]),
+    "wu_conv3x3_s2_dgrad": (I, [P, I, P, P, I, I, I, I, P]),
+    "wu_conv3x3_s2_wgrad_workspace_bytes": (SZ, [I, I, I, I, I]),
+    "wu_conv3x3_s2_wgrad": (I, [P, I, P, I, I, I, I, P, P, P, SZ, P]),
     "wu_adam_multi": (I, [P, P, I, F, F, F, F, F, I, P]),
     "wu_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
     "wu_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),

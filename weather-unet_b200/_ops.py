@@ -279,6 +279,99 @@ def disc_stem(x, w0, b0, w1, b1, slope):
     return _DiscStem.apply(x, w0, b0, w1, b1, slope)
 
 
+def conv3x3_s2(src, w_packed, bias, slope, cout):
+    """3x3 / stride 2 / pad 1 convolution + bias + LeakyReLU(slope) (slope 1 = none); see
+    wu_conv3x3_s2_fprop.  src (B,H,W,cin) -> (B,ceil(H/2),ceil(W/2),cout)."""
+    B, H, W, cin = src.shape
+    dst = _act(B, (H + 1) // 2, (W + 1) // 2, cout, src)
+    call("wu_conv3x3_s2_fprop", ptr(src), cin, ptr(w_packed), ptr(bias), float(slope), ptr(dst), cout,
+         B, H, W, stream())
+    return dst
+
+
+def conv3x3_s2_dgrad(dy, w_dgrad, cin, H, W):
+    """Data gradient of the stride-2 convolution: dy (B,Ho,Wo,cout) -> dx (B,H,W,cin)."""
+    B, Ho, Wo, cout = dy.shape
+    assert Ho == (H + 1) // 2 and Wo == (W + 1) // 2
+    dx = _act(B, H, W, cin, dy)
+    call("wu_conv3x3_s2_dgrad", ptr(dy), cout, ptr(w_dgrad), ptr(dx), cin, B, H, W, stream())
+    return dx
+
+
+def conv3x3_s2_wgrad(src, dy, want_bias=True):
+    """-> (dw fp32 [cout][cin][3][3], db fp32 [cout] or None) of the stride-2 convolution."""
+    B, H, W, cin = src.shape
+    cout = dy.shape[3]
+    nbytes = query("wu_conv3x3_s2_wgrad_workspace_bytes", cin, cout, B, H, W)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dy.device)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dy.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=dy.device) if want_bias else None
+    call("wu_conv3x3_s2_wgrad", ptr(src), cin, ptr(dy), cout, B, H, W, ptr(dw), ptr(db), ptr(ws),
+         nbytes, stream())
+    return dw, db
+
+
+class _DiscBlock(torch.autograd.Function):
+    """One discriminator block (nets.py:26-33) with cin >= 64 on the tcgen05 kernels:
+    x (B,cin,H,W) bf16 channels_last -> Conv3x3(cin,cin)+bias -> Conv3x3(cin,cout,stride 2)+bias ->
+    LeakyReLU -> (B,cout,H/2,W/2) bf16 channels_last.  Weights arrive spectrally normalised (fp32);
+    their gradients flow back into the spectral-norm graph (weight_orig, sigma) on the torch side."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1, slope):
+        xn = x.permute(0, 2, 3, 1)  # NHWC view of channels_last memory
+        if xn.dtype != BF16 or not xn.is_contiguous():
+            xn = xn.to(BF16).contiguous()
+        B, H, W, cin = xn.shape
+        cout = w1.shape[0]
+        w0f, w0d = pack_conv3x3_weights(w0.detach().float().contiguous())
+        w1f, w1d = pack_conv3x3_weights(w1.detach().float().contiguous())
+        h = conv3x3(xn, None, w0f, b0.detach().float(), False, None, cin)  # no activation (nets.py:28-29)
+        y = conv3x3_s2(h, w1f, b1.detach().float(), slope, cout)
+        ctx.save_for_backward(xn, h, y, w0d, w1d)
+        ctx.slope = float(slope)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, h, y, w0d, w1d = ctx.saved_tensors
+        B, H, W, cin = xn.shape
+        cout = y.shape[3]
+        dev = xn.device
+        need_x, need_w0, need_b0, need_w1, need_b1 = ctx.needs_input_grad[:5]
+        gy = gy.permute(0, 2, 3, 1)
+        if gy.dtype != BF16 or not gy.is_contiguous():
+            gy = gy.to(BF16).contiguous()
+        g = torch.empty_like(gy)
+        db1 = torch.empty((cout,), dtype=torch.float32, device=dev)
+        nb = query("wu_bias_act_bwd_workspace_bytes", cout)
+        ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+        call("wu_bias_act_bwd", ptr(gy), ptr(y), ptr(g), ptr(db1), ctx.slope, B * y.shape[1] * y.shape[2],
+             cout, ptr(ws), nb, stream())
+        dw1 = conv3x3_s2_wgrad(h, g, want_bias=False)[0] if need_w1 else None
+        gx = dw0 = db0 = None
+        if need_x or need_w0 or need_b0:
+            gh = conv3x3_s2_dgrad(g, w1d, cin, H, W)
+            if need_w0 or need_b0:
+                dw0, db0 = conv3x3_wgrad(xn, None, gh, want_bias=True)
+            if need_x:
+                gx = conv3x3(gh, None, w0d, None, False, None, cin).permute(0, 3, 1, 2)
+        return (gx, dw0 if need_w0 else None, db0 if need_b0 else None, dw1,
+                db1 if need_b1 else None, None)
+
+
+def disc_block_supported(x):
+    """bf16 channels_last CUDA activation whose channel count the tcgen05 kernels take."""
+    C = x.shape[1]
+    return (x.is_cuda and x.dim() == 4 and x.dtype == BF16 and C in (64, 128, 256)
+            and x.shape[2] >= 2 and x.shape[3] >= 2
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def disc_block(x, w0, b0, w1, b1, slope):
+    return _DiscBlock.apply(x, w0, b0, w1, b1, slope)
+
+
 def nchw_to_nhwc(x):
     """fp32 NCHW -> bf16 NHWC."""
     B, C, H, W = x.shape

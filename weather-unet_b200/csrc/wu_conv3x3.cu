@@ -1213,7 +1213,7 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
     if (splits > num_sms()) splits = num_sms();
     pl.splits = splits;
     pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
-    pl.bias_blocks = 148 * 4;
+    pl.bias_blocks = kBiasGradBlocks;
     pl.bias_bytes = (size_t)pl.bias_blocks * cout * sizeof(float);
     return pl;
   }
@@ -1233,7 +1233,7 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
   if (splits > 128) splits = 128;
   pl.splits = splits;
   pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
-  pl.bias_blocks = 148 * 4;
+  pl.bias_blocks = kBiasGradBlocks;
   pl.bias_bytes = (size_t)pl.bias_blocks * cout * sizeof(float);
   return pl;
 }
@@ -1371,30 +1371,36 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
   }
 }
 
-// split-K fold into the reference layout + bias gradient
-static int wgrad_finish(const float* partial, float* dw, float* db, const void* dy, void* workspace,
-                        const WgradPlan& pl, int cin, int cout, int B, int H, int W,
-                        cudaStream_t st) {
+// split-K fold into the reference layout + bias gradient (shared with wu_conv_s2.cu)
+namespace wu {
+int wgrad_fold(const float* partial, int splits, int cin, int cout, float* dw, const void* dy,
+               long long npix, float* db, float* bias_scratch, cudaStream_t st) {
   {
     const long long total = 9LL * cin * cout;
     int g = (int)((total + 255) / 256);
     if (g > 148 * 16) g = 148 * 16;
-    wgrad_reduce_kernel<<<g, 256, 0, st>>>(partial, dw, pl.splits, cin, cout);
+    wgrad_reduce_kernel<<<g, 256, 0, st>>>(partial, dw, splits, cin, cout);
     WU_CHECK_LAUNCH("wgrad_reduce_kernel");
   }
   if (db != nullptr) {
-    float* bpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.partial_bytes);
-    const long long npix = (long long)B * H * W;
     const int lanes = cout / 8;
     const int groups = 256 / lanes;
-    WU_REQUIRE(groups >= 1, "wu_conv3x3_wgrad: cout=%d too wide for the bias-grad kernel", cout);
-    bias_grad_partial_kernel<<<pl.bias_blocks, 256, groups * cout * sizeof(float), st>>>(
-        (const __nv_bfloat16*)dy, bpart, npix, cout);
+    WU_REQUIRE(groups >= 1, "wgrad: cout=%d too wide for the bias-grad kernel", cout);
+    bias_grad_partial_kernel<<<kBiasGradBlocks, 256, groups * cout * sizeof(float), st>>>(
+        (const __nv_bfloat16*)dy, bias_scratch, npix, cout);
     WU_CHECK_LAUNCH("bias_grad_partial_kernel");
-    bias_grad_final_kernel<<<(cout + 31) / 32, 256, 0, st>>>(bpart, db, pl.bias_blocks, cout);
+    bias_grad_final_kernel<<<(cout + 31) / 32, 256, 0, st>>>(bias_scratch, db, kBiasGradBlocks, cout);
     WU_CHECK_LAUNCH("bias_grad_final_kernel");
   }
   return WU_OK;
+}
+}  // namespace wu
+
+static int wgrad_finish(const float* partial, float* dw, float* db, const void* dy, void* workspace,
+                        const WgradPlan& pl, int cin, int cout, int B, int H, int W,
+                        cudaStream_t st) {
+  float* bpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.partial_bytes);
+  return wgrad_fold(partial, pl.splits, cin, cout, dw, dy, (long long)B * H * W, db, bpart, st);
 }
 
 extern "C" size_t wu_conv3x3_wgrad_workspace_bytes(int cin_total, int cout, int B, int H, int W) {

@@ -63,6 +63,31 @@ int make_act_tmap(CUtensorMap* out, const void* ptr, int B, int H, int W, int c,
   return WU_OK;
 }
 
+int make_act_tmap_strided(CUtensorMap* out, const void* ptr, int B, int Hv, int Wv, int c,
+                          long long pitch_w_bytes, long long pitch_h_bytes, long long pitch_b_bytes,
+                          int bw, int bh) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
+    return fail(WU_ERR_INVALID, "activation pointer %p not 16-byte aligned", ptr);
+  if (c % 64 != 0 || pitch_w_bytes % 16 != 0 || pitch_h_bytes % 16 != 0 || pitch_b_bytes % 16 != 0)
+    return fail(WU_ERR_INVALID, "strided activation view needs c %% 64 == 0 (got %d) and 16-byte pitches", c);
+  if (B <= 0 || Hv <= 0 || Wv <= 0)
+    return fail(WU_ERR_INVALID, "strided activation view is empty (B=%d Hv=%d Wv=%d)", B, Hv, Wv);
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch_w_bytes, (cuuint64_t)pitch_h_bytes,
+                           (cuuint64_t)pitch_b_bytes};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled(strided act B=%d Hv=%d Wv=%d c=%d box=%dx%d) -> %d",
+                B, Hv, Wv, c, bw, bh, (int)r);
+  return WU_OK;
+}
+
 int make_mat_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

@@ -39,6 +39,20 @@ void pick_box(int H, int W, int npix, int* bw, int* bh);
 
 int num_sms();
 
+// Strided NHWC bf16 view (e.g. the even/odd row/column "parity" views a stride-2 convolution walks):
+// dims (c, Wv, Hv, B) with byte pitches between consecutive view columns / rows / images; `ptr`
+// addresses element (0, 0, 0, 0) of the view.  Box (64, bw, bh, 1), 128-byte swizzle.
+int make_act_tmap_strided(CUtensorMap* out, const void* ptr, int B, int Hv, int Wv, int c,
+                          long long pitch_w_bytes, long long pitch_h_bytes, long long pitch_b_bytes,
+                          int bw, int bh);
+
+// Split-K fold of weight-gradient partials [splits][9*cin][cout] into dw [cout][cin][3][3] and,
+// when db != NULL, the bias gradient db[c] = sum_px dy[px][c] (dy bf16 [npix][cout]) through
+// `bias_scratch` (kBiasGradBlocks * cout floats).  Defined in wu_conv3x3.cu.
+constexpr int kBiasGradBlocks = 148 * 4;
+int wgrad_fold(const float* partial, int splits, int cin, int cout, float* dw, const void* dy,
+               long long npix, float* db, float* bias_scratch, cudaStream_t st);
+
 // Launch accounting behind wu_launch_count().
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }

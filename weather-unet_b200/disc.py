@@ -3,6 +3,8 @@ It is part of the measured G+D step but not of the generator hot path (SURVEY §
 on PyTorch until the generator rows meet their bar.  Same sub-module names and state_dict keys
 (`conv{1..4}.{0,1}.weight_orig/_u/_v`, `l.*`, `embed.*`), same init (disc.py:16-25), same return
 list [out, c1, c2, c3, c4]."""
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -65,6 +67,28 @@ class SNDisc(nn.Module):
             return K.disc_stem(x, c0.weight.float(), c0.bias.float(), c1.weight.float(),
                                c1.bias.float(), act.negative_slope)
 
+    @staticmethod
+    def _block(blk, h):
+        """conv2..conv4 blocks on the tcgen05 kernels (stride-1 implicit GEMM + the stride-2 /
+        LeakyReLU kernel of wu_conv_s2.cu, hand-written backward) when `h` is a bf16 channels_last
+        CUDA activation under bf16 autocast; None otherwise."""
+        try:
+            from . import _ops as K
+        except ImportError:
+            from weather_unet_b200 import _ops as K
+        if not (K.disc_block_supported(h) and torch.is_autocast_enabled()
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+            return None
+        if os.environ.get("WU_DISC_TRUNK", "") == "cudnn":  # A/B measurements only
+            return None
+        c0, c1, act = blk[0], blk[1], blk[2]
+        for conv in (c0, c1):
+            for hook in conv._forward_pre_hooks.values():  # spectral norm: power iteration, W / sigma
+                hook(conv, (h,))
+        with torch.autocast("cuda", enabled=False):
+            return K.disc_block(h, c0.weight.float(), c0.bias.float(), c1.weight.float(),
+                                c1.bias.float(), act.negative_slope)
+
     def forward(self, x, c=None):
         feats = []
         h = self._stem(x)
@@ -76,8 +100,12 @@ class SNDisc(nn.Module):
             h = x
         for i in range(first, 5):
             blk = getattr(self, f"conv{i}")
-            h = self._sn_conv(blk[0], h, 1.0)                       # no activation in between
-            h = self._sn_conv(blk[1], h, blk[2].negative_slope)     # (nets.py:26-33)
+            fast = self._block(blk, h)
+            if fast is not None:
+                h = fast
+            else:
+                h = self._sn_conv(blk[0], h, 1.0)                       # no activation in between
+                h = self._sn_conv(blk[1], h, blk[2].negative_slope)     # (nets.py:26-33)
             feats.append(h)
         pooled = feats[-1].sum(dim=(2, 3))  # global SUM pool (disc.py:32)
         out = self.l(pooled)
