@@ -174,8 +174,11 @@ int wu_conv3to64_s2_fprop(const float* h1, const float* w, const float* bias, fl
 size_t wu_conv3to64_s2_wgrad_workspace_bytes(int B, int Hin, int Win);
 int wu_conv3to64_s2_wgrad(const float* h1, const void* g, float* dw, float* db, int B, int Hin,
                           int Win, void* workspace, size_t workspace_bytes, wu_stream_t stream);
+/* tcgen05 (N = 16, three live columns) over the four parity classes of g_h1; `workspace` holds the
+ * packed bf16 weights (wu_conv3to64_s2_dgrad_workspace_bytes, 128-byte aligned). */
+size_t wu_conv3to64_s2_dgrad_workspace_bytes(void);
 int wu_conv3to64_s2_dgrad(const void* g, const float* w, float* g_h1, int B, int Hin, int Win,
-                          wu_stream_t stream);
+                          void* workspace, size_t workspace_bytes, wu_stream_t stream);
 /* Backward of the 3->3 convolution: g_x fp32 NCHW (may be NULL), dw [3][3][3][3], db [3] (may be NULL). */
 size_t wu_conv3to3_bprop_workspace_bytes(void);
 int wu_conv3to3_bprop(const float* g_h1, const float* x, const float* w, float* g_x, float* dw,

@@ -135,91 +135,6 @@ conv3to3_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
 }
 
-// Data gradient of the stride-2 convolution: g NHWC bf16 [B][H/2][W/2][64] -> g_h1 fp32 NCHW
-// [B][3][H][W].  One 8-lane group per 2x2 block of h1 pixels (y = 2Y'+dy, x = 2X'+dx): the block
-// touches g at (Y'+a, X'+c), a, c in {0,1}, and uses each of the nine taps exactly once
-// (tap r serves dy = (r+1)%2 from a = (dy+1-r)/2), so there is no parity divergence; every lane
-// owns 8 of the 64 channels of g and the 12 results are folded over the 8 lanes with shuffles.
-__global__ void __launch_bounds__(256)
-conv3to64_s2_dgrad_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ w,
-                          float* __restrict__ gh, int B, int H, int W) {
-  __shared__ __align__(16) float ws[27][64];  // [ci*9 + r*3 + s][co]
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
-    const int co = i / 27, k = i - co * 27;
-    ws[k][co] = w[i];
-  }
-  __syncthreads();
-  const int Ho = H >> 1, Wo = W >> 1;
-  const long long HW = (long long)H * W;
-  const long long nblk = (long long)B * Ho * Wo;  // 2x2 blocks == stride-2 output pixels
-  const int sub = threadIdx.x & 7;
-  const long long gid = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
-  const bool valid = gid < nblk;
-  const long long id = valid ? gid : nblk - 1;
-  const int Xp = (int)(id % Wo);
-  const long long t = id / Wo;
-  const int Yp = (int)(t % Ho);
-  const long long b = t / Ho;
-  // g vectors at (Yp + a, Xp + c)
-  float gv[2][2][8];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int Y = Yp + a, X = Xp + c;
-      if (Y < Ho && X < Wo) {
-        unpack8p(__ldg(reinterpret_cast<const uint4*>(g + ((b * Ho + Y) * Wo + X) * 64 + sub * 8)),
-                 gv[a][c]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) gv[a][c][e] = 0.f;
-      }
-    }
-  float acc[2][2][3];  // [dy][dx][ci]
-#pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx)
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) acc[dy][dx][ci] = 0.f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int dy = (r + 1) & 1, a = (dy + 1 - r) >> 1;  // r=0: dy=1,a=1; r=1: dy=0,a=0; r=2: dy=1,a=0
-#pragma unroll
-    for (int s3 = 0; s3 < 3; ++s3) {
-      const int dx = (s3 + 1) & 1, c = (dx + 1 - s3) >> 1;
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float4* wr = reinterpret_cast<const float4*>(&ws[ci * 9 + r * 3 + s3][sub * 8]);
-        const float4 w0 = wr[0], w1 = wr[1];
-        float v = acc[dy][dx][ci];
-        v = fmaf(gv[a][c][0], w0.x, v); v = fmaf(gv[a][c][1], w0.y, v);
-        v = fmaf(gv[a][c][2], w0.z, v); v = fmaf(gv[a][c][3], w0.w, v);
-        v = fmaf(gv[a][c][4], w1.x, v); v = fmaf(gv[a][c][5], w1.y, v);
-        v = fmaf(gv[a][c][6], w1.z, v); v = fmaf(gv[a][c][7], w1.w, v);
-        acc[dy][dx][ci] = v;
-      }
-    }
-  }
-#pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx)
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        float v = acc[dy][dx][ci];
-#pragma unroll
-        for (int m = 1; m < 8; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-        acc[dy][dx][ci] = v;
-      }
-  // 12 results per group: lanes 0..2 write channel `sub` of the four pixels (8 B row segments)
-  if (valid && sub < 3) {
-    float* o = gh + (b * 3 + sub) * HW + (long long)(2 * Yp) * W + 2 * Xp;
-    *reinterpret_cast<float2*>(o) = make_float2(acc[0][0][sub], acc[0][1][sub]);
-    *reinterpret_cast<float2*>(o + W) = make_float2(acc[1][0][sub], acc[1][1][sub]);
-  }
-}
-
 // Backward of Conv2d(3,3,3,padding=1): g_x = conv_transpose(g_h1, w0) (optional), and per-block
 // partial sums of dw0[co][ci][r][s] = sum g_h1[co] * x[ci][shifted], db0[co] = sum g_h1[co].
 constexpr int kStemBwdBlocks = 148 * 8;
@@ -361,18 +276,6 @@ extern "C" int wu_conv3to3_fprop(const float* x, const float* w, const float* bi
   if (g > 148LL * 16) g = 148LL * 16;
   conv3to3_fprop_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W);
   WU_CHECK_LAUNCH("conv3to3_fprop_kernel");
-  return WU_OK;
-}
-extern "C" int wu_conv3to64_s2_dgrad(const void* g, const float* w, float* g_h1, int B, int Hin,
-                                     int Win, wu_stream_t stream) {
-  WU_REQUIRE(g && w && g_h1 && B > 0 && Hin > 0 && Win > 0, "wu_conv3to64_s2_dgrad: bad args");
-  WU_REQUIRE(Hin % 2 == 0 && Win % 2 == 0, "wu_conv3to64_s2_dgrad: need even Hin, Win");
-  const long long nblk = (long long)B * (Hin / 2) * (Win / 2);
-  const long long grid = (nblk + 31) / 32;  // 32 eight-lane groups per 256-thread block
-  WU_REQUIRE(grid < (1LL << 31), "wu_conv3to64_s2_dgrad: grid too large");
-  conv3to64_s2_dgrad_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)g, w, g_h1, B, Hin, Win);
-  WU_CHECK_LAUNCH("conv3to64_s2_dgrad_kernel");
   return WU_OK;
 }
 extern "C" size_t wu_conv3to3_bprop_workspace_bytes(void) {

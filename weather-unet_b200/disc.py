@@ -60,10 +60,10 @@ class SNDisc(nn.Module):
                 and torch.get_autocast_dtype("cuda") == torch.bfloat16):
             return None
         c0, c1, act = self.conv1[0], self.conv1[1], self.conv1[2]
-        for conv in (c0, c1):
-            for hook in conv._forward_pre_hooks.values():  # spectral norm of both weights
-                hook(conv, (x,))
         with torch.autocast("cuda", enabled=False):
+            for conv in (c0, c1):  # spectral norm of both weights, in fp32 like the reference
+                for hook in conv._forward_pre_hooks.values():
+                    hook(conv, (x,))
             return K.disc_stem(x, c0.weight.float(), c0.bias.float(), c1.weight.float(),
                                c1.bias.float(), act.negative_slope)
 
@@ -82,10 +82,10 @@ class SNDisc(nn.Module):
         if os.environ.get("WU_DISC_TRUNK", "") == "cudnn":  # A/B measurements only
             return None
         c0, c1, act = blk[0], blk[1], blk[2]
-        for conv in (c0, c1):
-            for hook in conv._forward_pre_hooks.values():  # spectral norm: power iteration, W / sigma
-                hook(conv, (h,))
         with torch.autocast("cuda", enabled=False):
+            for conv in (c0, c1):  # spectral norm (power iteration, W / sigma) in fp32 like the reference
+                for hook in conv._forward_pre_hooks.values():
+                    hook(conv, (h,))
             return K.disc_block(h, c0.weight.float(), c0.bias.float(), c1.weight.float(),
                                 c1.bias.float(), act.negative_slope)
 
@@ -107,8 +107,9 @@ class SNDisc(nn.Module):
                 h = self._sn_conv(blk[0], h, 1.0)                       # no activation in between
                 h = self._sn_conv(blk[1], h, blk[2].negative_slope)     # (nets.py:26-33)
             feats.append(h)
-        pooled = feats[-1].sum(dim=(2, 3))  # global SUM pool (disc.py:32)
-        out = self.l(pooled)
-        proj = self.embed(c)  # like the reference, c=None fails here (disc.py:34)
-        out = out + (proj * pooled).sum(dim=1, keepdim=True)
+        pooled = feats[-1].sum(dim=(2, 3), dtype=torch.float32)  # global SUM pool (disc.py:32)
+        with torch.autocast(x.device.type, enabled=False):  # projection head in fp32 (tiny GEMVs)
+            out = self.l(pooled)
+            proj = self.embed(c)  # like the reference, c=None fails here (disc.py:34)
+            out = out + (proj * pooled).sum(dim=1, keepdim=True)
         return [out] + feats
