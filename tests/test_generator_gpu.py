@@ -136,20 +136,24 @@ def test_against_oracle(cuda, B, H, W, nc, train):
         r_ac = rel(gac[name].flatten(), g32[name].flatten())
         cos_tf = torch.nn.functional.cosine_similarity(gm, gtf[name].flatten().float(), dim=0).item()
         r_q = rel(gm, gtfq[name].flatten())
-        report.append((name, r_tf, cos_tf, r_noise, r_32, r_ac, r_q))
+        cos_noise = torch.nn.functional.cosine_similarity(gtfq[name].flatten().float(),
+                                                          gtf[name].flatten().float(), dim=0).item()
+        report.append((name, r_tf, cos_tf, r_noise, r_32, r_ac, r_q, cos_noise))
     lines = [f"{name:24s} teacher-forced: ours vs bf16-emulating oracle {r_q:.3e} | ours vs fp32 oracle "
              f"{r_tf:.3e} cos {cos_tf:.5f} (bf16 oracle vs fp32 oracle {r_noise:.3e})"
              f" | end-to-end vs fp32: ours {r_32:.3e} (autocast-bf16 {r_ac:.3e})"
-             for name, r_tf, cos_tf, r_noise, r_32, r_ac, r_q in report]
+             for name, r_tf, cos_tf, r_noise, r_32, r_ac, r_q, _ in report]
     print("\n".join(lines))
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/grad_parity_B{B}_H{H}_W{W}_train{int(train)}.txt", "w") as f:
         f.write("\n".join(lines) + "\n")
-    for name, r_tf, cos_tf, r_noise, r_32, r_ac, r_q in report:
+    for name, r_tf, cos_tf, r_noise, r_32, r_ac, r_q, cos_noise in report:
         # same forward values, same storage precision: this is the kernel-chain parity proper
         assert r_q < 3e-2, f"{name}: vs teacher-forced bf16-emulating oracle rel-L2 {r_q:.3e}"
-        assert r_tf < 1.5 * r_noise + 2e-2 and cos_tf > 0.99, \
-            f"{name}: teacher-forced rel-L2 {r_tf:.3e} (noise {r_noise:.3e}) cos {cos_tf:.5f}"
+        # direction: as well aligned with fp32 as the bf16-emulating oracle itself is (0.99 when
+        # bf16 storage noise is small; on the deepest biases of small cases that oracle sits at 0.985)
+        assert r_tf < 1.5 * r_noise + 2e-2 and cos_tf > min(0.99, cos_noise - 2e-3), \
+            f"{name}: teacher-forced rel-L2 {r_tf:.3e} (noise {r_noise:.3e}) cos {cos_tf:.5f} ({cos_noise:.5f})"
         assert r_32 < 1.3 * r_ac + 2e-2, f"{name}: vs fp32 {r_32:.3e}, autocast-bf16 band {r_ac:.3e}"
 
 

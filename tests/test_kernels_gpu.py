@@ -171,7 +171,7 @@ def test_disc_block(cuda):
     assert max(errs.values()) < 1e-2, errs
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 24, 40), (3, 64, 64)])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 24, 40), (3, 64, 64), (2, 20, 18), (1, 256, 256)])
 def test_conv_first(cuda, B, H, W):
     from weather_unet_b200 import _ops as K
     g = torch.Generator(device="cpu").manual_seed(H)

@@ -1,0 +1,335 @@
+// wu_conv_first_tc.cu — the K = 27 convolutions that read a 3-channel fp32 NCHW image, on tcgen05:
+//   * generator first layer  Conv2d(3, 64, 3, padding=1) + ReLU            (cunet.py:21,45; nets.py:20-21)
+//   * discriminator stem     Conv2d(3, 64, 3, padding=1, stride=2) + LeakyReLU (disc.py:12,28; nets.py:30-32)
+// As FMA kernels these layers were instruction bound (1728 FMAs per output pixel: ~0.5 ms for
+// 64 x 256 x 256 pixels against 0.08 ms of HBM time for the 537 MB they write).  Here the 3x3x3 patch
+// of every output pixel is written by producer threads as ONE 128-byte row of TF32 words
+// (k = ci*9 + r*3 + s, 27 live + 5 zero) in the 128B-swizzled K-major layout the tensor core reads,
+// the [64][32] weight matrix stays resident in shared memory, and a tile of 128 pixels is four
+// tcgen05.mma.kind::tf32 (M = 128, N = 64, K = 8) into TMEM.  TF32 keeps 11 significant bits of the
+// image and the weights (rounded to nearest), well inside the bf16 rounding of the output.
+// Warp roles: 0 = TMA producer of raw image boxes (3 channels x ((bh-1)*S+3) rows x (bw*S+8) columns of
+// fp32, halo zero-filled by TMA), 1-4 = im2col (one pixel row each, shared -> shared), 5 = MMA
+// issuer, 6-9 = epilogue (TMEM -> bias -> ReLU / LeakyReLU -> bf16 -> swizzled staging -> TMA store).
+// The raw boxes decouple the global-memory latency from the im2col threads (a first version that
+// loaded the 27 values straight from global memory ran one tile per ~2.5 us per SM: latency bound);
+// that direct path remains for images whose row pitch is not a multiple of 16 bytes (TMA limit).
+#include <cstdlib>
+
+#include "wu_host.h"
+#include "wu_ptx.cuh"
+
+namespace wu {
+
+struct K27Params {
+  const float* x;     // [B][3][Hin][Win]
+  const float* w;     // [64][27]
+  const float* bias;  // [64] or null
+  int Hin, Win, Ho, Wo;
+  int bw, bh, log2_bw;  // output pixel box of a tile, bw * bh == 128
+  int bx, by;           // raw input box: bx = bw*S + 8 columns (16-byte aligned start), by = (bh-1)*S + 3 rows
+  int tiles_w, tiles_h, num_tiles;
+  float slope;          // v > 0 ? v : v * slope  (0 = ReLU)
+};
+
+constexpr int kK27Stages = 4;
+constexpr int kK27ABytes = 128 * 128;
+constexpr int kK27BBytes = 64 * 128;
+constexpr int kK27RawBytes = 10240;
+constexpr int kK27Smem =
+    kK27Stages * kK27ABytes + kK27BBytes + 2 * 16384 + kK27Stages * kK27RawBytes + 1024 + 1024;
+
+template <int STRIDE, bool TMA_IN>
+__global__ void __launch_bounds__(320, 1)
+conv_k27_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
+                      const K27Params p) {
+  constexpr int S = kK27Stages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t b_base = base + S * kK27ABytes;
+  const uint32_t staging_base = b_base + kK27BBytes;
+  const uint32_t raw_base = staging_base + 2 * 16384;
+  const uint32_t bar_base = raw_base + S * kK27RawBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto rempty_bar = [&](int s) { return bar_base + 8u * (3 * S + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (4 * S + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (4 * S + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (4 * S + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmD);
+    if (TMA_IN) tma_prefetch_desc(&tmX);
+  }
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(rfull_bar(s), 1);
+      mbar_init(rempty_bar(s), 128);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    fence_mbar_init();
+  }
+  // weights -> shared memory, K-major rows of 128 B (32 tf32 words), 16-byte chunks XOR-swizzled
+  for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+    const int co = i >> 5, k = i & 31;
+    const float v = k < 27 ? to_tf32(__ldg(p.w + co * 27 + k)) : 0.f;
+    *reinterpret_cast<float*>(smem + (b_base - base) + co * 128 + (((k >> 2) ^ (co & 7)) << 4) +
+                              (k & 3) * 4) = v;
+  }
+  fence_proxy_async_smem();
+  if (warp == 6) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int tile, int& b, int& h0, int& w0) {
+    const int tw = tile % p.tiles_w;
+    const int t2 = tile / p.tiles_w;
+    const int th = t2 % p.tiles_h;
+    b = t2 / p.tiles_h;
+    h0 = th * p.bh;
+    w0 = tw * p.bw;
+  };
+
+  if (warp == 0) {
+    if (TMA_IN && lane == 0) {
+      // ---------------------------------------------------------------- raw image boxes by TMA
+      const uint32_t bytes = (uint32_t)(p.bx * p.by * 3 * 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int b, h0, w0;
+        decode(tile, b, h0, w0);
+        mbar_wait(rempty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(rfull_bar(stage), bytes);
+        // the innermost start coordinate of a non-swizzled fp32 box must be a multiple of 4 elements
+        // (16 bytes; anything else faults): start 4 columns to the left instead of 1
+        tma_load_4d(raw_base + stage * kK27RawBytes, &tmX, rfull_bar(stage), w0 * STRIDE - 4,
+                    h0 * STRIDE - 1, 0, b);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp < 5) {
+    // ------------------------------------------------------------------ im2col (one pixel row each)
+    const int row = threadIdx.x - 32;  // 0..127: pixel of the tile == A row == TMEM lane
+    const int ph = row >> p.log2_bw, pw = row & (p.bw - 1);
+    const size_t plane = (size_t)p.Hin * p.Win;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int b, h0, w0;
+      decode(tile, b, h0, w0);
+      float v[32];
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0.f;
+      if (TMA_IN) {
+        mbar_wait(rfull_bar(stage), phase);
+        const float* rt = reinterpret_cast<const float*>(smem + (raw_base - base) + stage * kK27RawBytes);
+        const int cstride = p.bx * p.by;
+        const float* r0 = rt + (ph * STRIDE) * p.bx + pw * STRIDE + 3;  // raw column 0 is image column w0*S - 4
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) v[ci * 9 + r * 3 + s] = to_tf32(r0[ci * cstride + r * p.bx + s]);
+        mbar_arrive(rempty_bar(stage));  // values are in registers: the raw slot may be refilled
+      } else {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) v[k] = 0.f;
+        const int ho = h0 + ph, wo = w0 + pw;
+        if (ho < p.Ho && wo < p.Wo) {
+          const float* xb = p.x + (size_t)b * 3 * plane;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const int hh = ho * STRIDE + r - 1;
+            if (hh < 0 || hh >= p.Hin) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const int ww = wo * STRIDE + s - 1;
+              if (ww < 0 || ww >= p.Win) continue;
+              const float* src = xb + (size_t)hh * p.Win + ww;
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci) v[ci * 9 + r * 3 + s] = to_tf32(__ldg(src + ci * plane));
+            }
+          }
+        }
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* arow = smem + stage * kK27ABytes + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(arow + ((c ^ (row & 7)) << 4)) =
+            make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(stage));
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // -------------------------------------------------------------- MMA issuer (one thread)
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      const uint64_t adesc0 = umma_smem_desc_sw128(base, 16, 1024);
+      const uint64_t bdesc0 = umma_smem_desc_sw128(b_base, 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint64_t soff = (uint64_t)((stage * kK27ABytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 words = 32 bytes)
+          umma_tf32(tmem_base + buf * 64, adesc0 + soff + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * 2),
+                    idesc, k != 0 ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(buf));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (warps 6..9)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 192);
+    const float slope = p.slope;
+    uint32_t store_count = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int b, h0, w0;
+      decode(tile, b, h0, w0);
+      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64;
+      tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + j));
+        float f0 = __uint_as_float(v[j + 0]) + bv.x, f1 = __uint_as_float(v[j + 1]) + bv.y;
+        float f2 = __uint_as_float(v[j + 2]) + bv.z, f3 = __uint_as_float(v[j + 3]) + bv.w;
+        f0 = f0 > 0.f ? f0 : f0 * slope;
+        f1 = f1 > 0.f ? f1 : f1 * slope;
+        f2 = f2 > 0.f ? f2 : f2 * slope;
+        f3 = f3 > 0.f ? f3 : f3 * slope;
+        pk[j / 2] = pack_bf16x2(f0, f1);
+        pk[j / 2 + 1] = pack_bf16x2(f2, f3);
+      }
+      const uint32_t sb = staging_base + (store_count & 1u) * 16384u;
+      ++store_count;
+      if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+      named_bar_sync(1, 128);
+      uint8_t* srow = smem + (sb - base) + row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (issuer) {
+        tma_store_4d(&tmD, sb, 0, w0, h0, b);  // pixels outside the image are clipped by the map
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) tmem_dealloc<128>(tmem_base);
+}
+
+template <int STRIDE, bool TMA_IN>
+static int launch_k27(const CUtensorMap& xm, const CUtensorMap& dm, const K27Params& p,
+                      cudaStream_t st) {
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv_k27_fprop_kernel<STRIDE, TMA_IN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kK27Smem));
+    attr_done = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  conv_k27_fprop_kernel<STRIDE, TMA_IN><<<grid, 320, kK27Smem, st>>>(xm, dm, p);
+  WU_CHECK_LAUNCH("conv_k27_fprop_kernel");
+  return WU_OK;
+}
+
+int conv_k27_fprop_tc(const float* x, const float* w, const float* bias, float slope, void* dst, int B,
+                      int Hin, int Win, int stride, cudaStream_t st) {
+  K27Params p;
+  p.x = x;
+  p.w = w;
+  p.bias = bias;
+  p.Hin = Hin;
+  p.Win = Win;
+  p.Ho = stride == 2 ? (Hin + 1) / 2 : Hin;
+  p.Wo = stride == 2 ? (Win + 1) / 2 : Win;
+  // output pixel box: bw * bh == 128, bw a power of two (<= 64 for stride 2: the raw box is 2*bw+4
+  // columns and a TMA box dimension is at most 256), least padded area, widest on ties
+  long best = -1;
+  for (int bw = (stride == 2 ? 64 : 128); bw >= 8; bw >>= 1) {
+    const int bh = 128 / bw;
+    const long padded = (long)((p.Wo + bw - 1) / bw) * bw * (long)((p.Ho + bh - 1) / bh) * bh;
+    if (best < 0 || padded < best) {
+      best = padded;
+      p.bw = bw;
+      p.bh = bh;
+    }
+  }
+  p.log2_bw = 0;
+  while ((1 << p.log2_bw) < p.bw) ++p.log2_bw;
+  p.bx = p.bw * stride + 8;  // image columns w0*S - 4 .. w0*S + bw*S + 3
+  p.by = (p.bh - 1) * stride + 3;
+  WU_REQUIRE(p.bx * p.by * 12 <= kK27RawBytes, "first-layer convolution: raw box %dx%d too large", p.bx, p.by);
+  p.tiles_w = (p.Wo + p.bw - 1) / p.bw;
+  p.tiles_h = (p.Ho + p.bh - 1) / p.bh;
+  const long long nt = (long long)B * p.tiles_w * p.tiles_h;
+  WU_REQUIRE(nt > 0 && nt < (1LL << 31), "first-layer convolution: too many tiles");
+  p.num_tiles = (int)nt;
+  p.slope = slope;
+  CUtensorMap dm, xm;
+  int rc;
+  if ((rc = make_act_tmap(&dm, dst, B, p.Ho, p.Wo, 64, 64, p.bw, p.bh)) != WU_OK) return rc;
+  static const bool tma_off = getenv("WU_K27_TMA") != nullptr && atoi(getenv("WU_K27_TMA")) == 0;
+  const bool tma_in = !tma_off && (Win % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (tma_in) {
+    if ((rc = make_image_tmap(&xm, x, B, 3, Hin, Win, p.bx, p.by)) != WU_OK) return rc;
+    return stride == 2 ? launch_k27<2, true>(xm, dm, p, st) : launch_k27<1, true>(xm, dm, p, st);
+  }
+  xm = dm;
+  return stride == 2 ? launch_k27<2, false>(xm, dm, p, st) : launch_k27<1, false>(xm, dm, p, st);
+}
+
+}  // namespace wu

@@ -119,136 +119,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
 // ------------------------------------------------------------------------------------------------
 // first layer: Conv2d(3, 64, 3, padding=1) + ReLU, NCHW fp32 image -> NHWC bf16
 // ------------------------------------------------------------------------------------------------
-// thread = (pixel, 16-channel group); a warp writes 8 pixels x 128 B contiguous.
-__global__ void __launch_bounds__(256)
-conv_first_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int B, int H,
-                        int W) {
-  __shared__ __align__(16) float ws[27][64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
-    const int co = i / 27, k = i - co * 27;  // w is [co][ci][r][s] = [co][k]
-    ws[k][co] = w[i];
-  }
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.f;
-  __syncthreads();
-  const long long npix = (long long)B * H * W;
-  const int cg = threadIdx.x & 3;
-  for (long long px = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); px < npix;
-       px += (long long)gridDim.x * 64) {
-    const int wq = (int)(px % W);
-    const long long t = px / W;
-    const int hq = (int)(t % H);
-    const int b = (int)(t / H);
-    float in[27];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int hh = hq + r - 1, ww = wq + s - 1;
-          in[ci * 9 + r * 3 + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                                       ? __ldg(x + (((long long)b * 3 + ci) * H + hh) * W + ww)
-                                       : 0.f;
-        }
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = bs[cg * 16 + j];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4* wr = reinterpret_cast<const float4*>(&ws[k][cg * 16]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 wv = wr[j];
-        acc[4 * j + 0] = fmaf(in[k], wv.x, acc[4 * j + 0]);
-        acc[4 * j + 1] = fmaf(in[k], wv.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(in[k], wv.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(in[k], wv.w, acc[4 * j + 3]);
-      }
-    }
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-    uint4* o = reinterpret_cast<uint4*>(dst + px * 64 + cg * 16);
-    o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-  }
-}
-
-// Register-tiled variant for W % 4 == 0: thread = 4 consecutive output pixels of a row x 8 channels
-// (32 accumulators, inputs in registers), 8 threads cover the 64 channels of a pixel quad.
-// STRIDE 1: the generator's first layer (ReLU = slope 0).  STRIDE 2: the discriminator stem's
-// Conv2d(3, 64, 3, padding=1, stride=2) + LeakyReLU (nets.py:30-32); H, W are OUTPUT sizes.
-template <int STRIDE>
-__global__ void __launch_bounds__(256)
-conv_first_fprop_x4_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int B,
-                           int H, int W, float slope) {
-  constexpr int NC = 3 * STRIDE + 3;  // input columns feeding 4 adjacent outputs
-  __shared__ __align__(16) float ws[27][64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
-    const int co = i / 27, k = i - co * 27;
-    ws[k][co] = w[i];
-  }
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.f;
-  __syncthreads();
-  const int Hin = H * STRIDE, Win = W * STRIDE;
-  const int Wq = W >> 2;
-  const long long nquad = (long long)B * H * Wq;
-  const int cg = threadIdx.x & 7;
-  for (long long qd = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); qd < nquad;
-       qd += (long long)gridDim.x * 32) {
-    const int wq = (int)(qd % Wq) * 4;
-    const long long t = qd / Wq;
-    const int hq = (int)(t % H);
-    const int b = (int)(t / H);
-    float in[3][3][NC];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int hh = hq * STRIDE + r - 1;
-        const float* row = x + (((long long)b * 3 + ci) * Hin + hh) * Win;
-        const bool hv = hh >= 0 && hh < Hin;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int ww = wq * STRIDE + c - 1;
-          in[ci][r][c] = (hv && ww >= 0 && ww < Win) ? __ldg(row + ww) : 0.f;
-        }
-      }
-    float acc[4][8];
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[p][j] = bs[cg * 8 + j];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) {
-          const float4* wr = reinterpret_cast<const float4*>(&ws[ci * 9 + r * 3 + s3][cg * 8]);
-          const float4 w0 = wr[0], w1 = wr[1];
-          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float xv = in[ci][r][p * STRIDE + s3];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xv, wv[j], acc[p][j]);
-          }
-        }
-    const long long px0 = ((long long)b * H + hq) * W + wq;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = acc[p][j] > 0.f ? acc[p][j] : acc[p][j] * slope;
-      *reinterpret_cast<uint4*>(dst + (px0 + p) * 64 + cg * 8) = pack8(o);
-    }
-  }
-}
+// (the forward pass lives in wu_conv_first_tc.cu: TF32 im2col rows on tcgen05)
 
 // dw[co][k] = sum_px dy[px][co] * patch[px][k]  (k = ci*9 + r*3 + s, slot 27 == 1 -> db).
 // Block: 256 threads = 4 pixel slices x (16 channel quads x 4 tap octets); 32 accumulators/thread.
@@ -1076,17 +947,7 @@ extern "C" int wu_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int 
 extern "C" int wu_conv_first_fprop(const float* x, const float* w, const float* bias, void* dst,
                                    int B, int H, int W, wu_stream_t stream) {
   WU_REQUIRE(x && w && dst && B > 0 && H > 0 && W > 0, "wu_conv_first_fprop: bad args");
-  const long long npix = (long long)B * H * W;
-  if (W % 4 == 0) {
-    conv_first_fprop_x4_kernel<1><<<grid_for(npix / 4, 32, 16), 256, 0, (cudaStream_t)stream>>>(
-        x, w, bias, (bf16*)dst, B, H, W, 0.f);
-    WU_CHECK_LAUNCH("conv_first_fprop_x4_kernel");
-    return WU_OK;
-  }
-  conv_first_fprop_kernel<<<grid_for(npix, 64, 8), 256, 0, (cudaStream_t)stream>>>(
-      x, w, bias, (bf16*)dst, B, H, W);
-  WU_CHECK_LAUNCH("conv_first_fprop_kernel");
-  return WU_OK;
+  return conv_k27_fprop_tc(x, w, bias, 0.f, dst, B, H, W, 1, (cudaStream_t)stream);
 }
 static int first_wgrad_blocks(long long npix) {
   long long tiles = (npix + kFirstWgradTile - 1) / kFirstWgradTile;
@@ -1299,14 +1160,9 @@ extern "C" int wu_adain_bwd_apply(const void* gz, const void* x, const float* co
 extern "C" int wu_conv3to64_s2_fprop(const float* h1, const float* w, const float* bias, float slope,
                                      void* dst, int B, int Hin, int Win, wu_stream_t stream) {
   WU_REQUIRE(h1 && w && dst && B > 0 && Hin > 0 && Win > 0, "wu_conv3to64_s2_fprop: bad args");
-  WU_REQUIRE(Hin % 2 == 0 && Win % 8 == 0,
-             "wu_conv3to64_s2_fprop: need even Hin and Win %% 8 == 0 (got %d x %d)", Hin, Win);
-  const int H = Hin / 2, W = Win / 2;
-  const long long npix = (long long)B * H * W;
-  conv_first_fprop_x4_kernel<2><<<grid_for(npix / 4, 32, 16), 256, 0, (cudaStream_t)stream>>>(
-      h1, w, bias, (bf16*)dst, B, H, W, slope);
-  WU_CHECK_LAUNCH("conv_first_fprop_x4_kernel<2>");
-  return WU_OK;
+  WU_REQUIRE(Hin % 2 == 0 && Win % 2 == 0,
+             "wu_conv3to64_s2_fprop: need even Hin and Win (got %d x %d)", Hin, Win);
+  return conv_k27_fprop_tc(h1, w, bias, slope, dst, B, Hin, Win, 2, (cudaStream_t)stream);
 }
 extern "C" size_t wu_conv3to64_s2_wgrad_workspace_bytes(int B, int Hin, int Win) {
   if (B <= 0 || Hin <= 0 || Win <= 0) return 0;

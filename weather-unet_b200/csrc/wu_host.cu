@@ -88,6 +88,25 @@ int make_act_tmap_strided(CUtensorMap* out, const void* ptr, int B, int Hv, int 
   return WU_OK;
 }
 
+int make_image_tmap(CUtensorMap* out, const float* ptr, int B, int C, int H, int W, int bx, int by) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || W % 4 != 0 || bx % 4 != 0 || bx > 256 || by > 256)
+    return fail(WU_ERR_INVALID, "image map needs a 16-byte aligned pointer, W %% 4 == 0 and a box <= 256 (W=%d box=%dx%d)",
+                W, bx, by);
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)C, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled(image B=%d C=%d H=%d W=%d box=%dx%d) -> %d", B, C, H,
+                W, bx, by, (int)r);
+  return WU_OK;
+}
+
 int make_mat_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

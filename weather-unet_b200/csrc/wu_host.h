@@ -46,12 +46,21 @@ int make_act_tmap_strided(CUtensorMap* out, const void* ptr, int B, int Hv, int 
                           long long pitch_w_bytes, long long pitch_h_bytes, long long pitch_b_bytes,
                           int bw, int bh);
 
+// fp32 NCHW image [B][C][H][W] as a 4-D map (W, H, C, B), box (bx, by, C, 1), no swizzle, zero fill
+// outside the image.  Needs W % 4 == 0 (16-byte row pitch) and a 16-byte aligned pointer.
+int make_image_tmap(CUtensorMap* out, const float* ptr, int B, int C, int H, int W, int bx, int by);
+
 // Split-K fold of weight-gradient partials [splits][9*cin][cout] into dw [cout][cin][3][3] and,
 // when db != NULL, the bias gradient db[c] = sum_px dy[px][c] (dy bf16 [npix][cout]) through
 // `bias_scratch` (kBiasGradBlocks * cout floats).  Defined in wu_conv3x3.cu.
 constexpr int kBiasGradBlocks = 148 * 4;
 int wgrad_fold(const float* partial, int splits, int cin, int cout, float* dw, const void* dy,
                long long npix, float* db, float* bias_scratch, cudaStream_t st);
+
+// Conv2d(3, 64, 3, padding=1, stride) + bias + LeakyReLU(slope) of an fp32 NCHW image into NHWC bf16
+// on tcgen05 (TF32 im2col rows written by producer threads).  Defined in wu_conv_first_tc.cu.
+int conv_k27_fprop_tc(const float* x, const float* w, const float* bias, float slope, void* dst, int B,
+                      int Hin, int Win, int stride, cudaStream_t st);
 
 // Launch accounting behind wu_launch_count().
 extern std::atomic<unsigned long long> g_launches;
