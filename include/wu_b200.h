@@ -207,6 +207,30 @@ int wu_conv3x3_s2_wgrad(const void* src, int cin, const void* dy, int cout, int 
                         float* dw, float* db, void* workspace, size_t workspace_bytes,
                         wu_stream_t stream);
 
+/* ---- spectral normalisation of the discriminator's weights, multi-tensor -----------
+ * torch.nn.utils.spectral_norm as the reference applies it (nets.py:26-33, disc.py:21,24): one power
+ * iteration per training-mode forward on W [rows = out][cols = in*kh*kw] (fp32, contiguous),
+ *   v <- normalize(W^T u), u <- normalize(W v), sigma = u . (W v), W_sn = W / sigma   (eps on the norms);
+ * eval mode (training == 0) uses the stored u, v.  `tensors`: device array of records
+ *   {const float* w; float* u; float* v; float* u_snap; float* v_snap; float* sigma; float* t; float* s;
+ *    float* part; float* w_sn; const float* g; float* dw; int32 rows; int32 cols}          (104 bytes)
+ * with t [cols], s [rows], part [wu_sn_parts()] scratch; u_snap / v_snap / sigma are this forward's
+ * values, kept for the backward pass.  Work items {int32 tensor; int32 begin; int32 count; int32 index}:
+ *   wtu_chunks : begin = first column, wu_sn_wtu_cols() columns each, index = chunk number in its tensor
+ *   wv_chunks  : begin = first row, wu_sn_wv_rows() rows each, index = chunk number in its tensor
+ *   elem_chunks: begin / count in units of 1024 elements.
+ * Backward of W_sn = W / sigma(W) with u, v constant:  dw = g / sigma - (<g, w> / sigma^2) u v^T.
+ *   dot_chunks : like elem_chunks, at most wu_sn_parts()/2 per tensor, index = chunk number
+ *   bwd_chunks : like elem_chunks, index = that tensor's number of dot chunks. */
+int wu_sn_parts(void);
+int wu_sn_wtu_cols(void);
+int wu_sn_wv_rows(void);
+int wu_sn_forward(const void* tensors, int n_tensors, const void* wtu_chunks, int n_wtu_chunks,
+                  const void* wv_chunks, int n_wv_chunks, const void* elem_chunks, int n_elem_chunks,
+                  int training, float eps, wu_stream_t stream);
+int wu_sn_backward(const void* tensors, const void* dot_chunks, int n_dot_chunks,
+                   const void* bwd_chunks, int n_bwd_chunks, wu_stream_t stream);
+
 /* ---- multi-tensor Adam (t_cls_train.py:184-185) ---------------------------------
  * torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, no amsgrad)
  * for a whole parameter list in one launch.  `tensors`: device array of records

@@ -32,28 +32,73 @@ def test_bias_act(cuda, B, C, H, W, slope):
     assert ((bin_.grad - br.grad).norm() / br.grad.norm()).item() < 2e-3
 
 
+def test_fused_spectral_norm(cuda):
+    """wu_sn_forward / wu_sn_backward against torch.nn.utils.spectral_norm's hook (the reference's
+    mechanism): W / sigma, the updated u / v buffers over several training forwards, eval mode, and
+    the gradient w.r.t. weight_orig."""
+    import torch.nn as nn
+    from weather_unet_b200._spectral import FusedSpectralNorm
+
+    def make():
+        torch.manual_seed(3)
+        return [nn.utils.spectral_norm(nn.Conv2d(64, 128, 3, padding=1)).to(cuda),
+                nn.utils.spectral_norm(nn.Conv2d(3, 3, 3, padding=1)).to(cuda),
+                nn.utils.spectral_norm(nn.Conv2d(256, 512, 3, padding=1, stride=2)).to(cuda),
+                nn.utils.spectral_norm(nn.Linear(512, 1)).to(cuda),
+                nn.utils.spectral_norm(nn.Linear(5, 512)).to(cuda)]
+
+    mine, ref = make(), make()
+    sn = FusedSpectralNorm(mine)
+    assert sn.supported()
+    gen = torch.Generator().manual_seed(4)
+    for it in range(3):
+        training = it < 2
+        for m in mine + ref:
+            m.train(training)
+        ws = sn(training)
+        for m in ref:  # the hook: power iteration (training) + weight = weight_orig / sigma
+            for h in m._forward_pre_hooks.values():
+                h(m, None)
+        gs = [torch.randn(w.shape, generator=gen).to(cuda) for w in ws]
+        torch.autograd.backward(ws, gs)
+        torch.autograd.backward([m.weight for m in ref], gs)
+        for w, m, r in zip(ws, mine, ref):
+            assert torch.allclose(w, r.weight, rtol=2e-5, atol=1e-7), (it, w.shape)
+            assert torch.allclose(m.weight_u, r.weight_u, rtol=1e-4, atol=1e-6)
+            assert torch.allclose(m.weight_v, r.weight_v, rtol=1e-4, atol=1e-6)
+            e = ((m.weight_orig.grad - r.weight_orig.grad).norm() / r.weight_orig.grad.norm()).item()
+            assert e < 1e-5, (it, w.shape, e)
+            m.weight_orig.grad = None
+            r.weight_orig.grad = None
+
+
 def test_disc_fast_path(cuda):
-    """SNDisc under bf16 autocast + channels_last takes the fused kernels; outputs and gradients
-    agree with the plain PyTorch module path in the same precision."""
+    """SNDisc under bf16 autocast on an fp32 NCHW image runs entirely on the sm_100a kernels (fused
+    spectral norm, stem, tcgen05 trunk); outputs, gradients and the spectral-norm buffers agree with
+    the plain PyTorch module path in the same precision."""
     from weather_unet_b200.disc import SNDisc
     from weather_unet_b200 import _ops as K
     torch.manual_seed(100)
-    d1 = SNDisc(5).to(cuda).train().to(memory_format=torch.channels_last)
+    d1 = SNDisc(5).to(cuda).train()
     torch.manual_seed(100)
     d2 = SNDisc(5).to(cuda).train().to(memory_format=torch.channels_last)
-    x = (torch.rand(4, 3, 64, 64, device=cuda) * 2 - 1).contiguous(memory_format=torch.channels_last)
+    x = torch.rand(4, 3, 64, 64, device=cuda) * 2 - 1
     c = torch.eye(5, device=cuda)[:4]
     n0 = K.launch_count()
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        o1 = d1(x, c)[0].float()
-    assert K.launch_count() > n0, "fast path not taken"
+        res = d1(x, c)
+    o1 = res[0].float()
+    assert K.launch_count() - n0 >= 4 + 2 + 3 * 4, "kernel path not taken"
+    assert [tuple(f.shape) for f in res[1:]] == [(4, 64, 32, 32), (4, 128, 16, 16), (4, 256, 8, 8), (4, 512, 4, 4)]
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        h = x
+        h = x.contiguous(memory_format=torch.channels_last)
         for i in range(1, 5):
-            h = getattr(d2, f"conv{i}")(h)  # plain nn.Sequential path
+            h = getattr(d2, f"conv{i}")(h)  # plain nn.Sequential path (cuDNN)
         pooled = h.sum(dim=(2, 3))
         o2 = (d2.l(pooled) + (d2.embed(c) * pooled).sum(1, keepdim=True)).float()
     assert torch.allclose(o1, o2, rtol=3e-2, atol=3e-2 * o2.abs().max().item())
+    for (n, b1), (_, b2) in zip(d1.named_buffers(), d2.named_buffers()):
+        assert torch.allclose(b1, b2, rtol=2e-2, atol=2e-3), n  # d2's power iteration ran in bf16
     o1.sum().backward()
     o2.sum().backward()
     for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):

@@ -58,6 +58,11 @@ SIGNATURES = {
     "wu_conv3x3_s2_dgrad": (I, [P, I, P, P, I, I, I, I, P]),
     "wu_conv3x3_s2_wgrad_workspace_bytes": (SZ, [I, I, I, I, I]),
     "wu_conv3x3_s2_wgrad": (I, [P, I, P, I, I, I, I, P, P, P, SZ, P]),
+    "wu_sn_parts": (I, []),
+    "wu_sn_wtu_cols": (I, []),
+    "wu_sn_wv_rows": (I, []),
+    "wu_sn_forward": (I, [P, I, P, I, P, I, P, I, I, F, P]),
+    "wu_sn_backward": (I, [P, P, I, P, I, P]),
     "wu_adam_multi": (I, [P, P, I, F, F, F, F, F, I, P]),
     "wu_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
     "wu_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),

@@ -4,8 +4,8 @@ t_est_train.py:214-283 is the same skeleton with real-valued conditions), restat
 or user-supplied batches, single GPU or data parallel (one process per GPU, NCCL all-reduce of the
 gradient buckets overlapped with backward).
 
-The generator runs on the sm_100a kernels; the discriminator and the optional frozen
-estimator are ordinary PyTorch modules.
+The generator and the discriminator run on the sm_100a kernels (the discriminator under bf16
+autocast); the optional frozen estimator is an ordinary PyTorch module.
 """
 import torch
 import torch.distributed as dist
@@ -128,8 +128,10 @@ class GDTrainStep:
         #  and saves one generator forward.  Default: faithful.
         self.share_fake = share_fake
         self.d_autocast = d_autocast
-        self.d_channels_last = next(D.parameters()).is_cuda
-        if self.d_channels_last:  # cuDNN's bf16 tensor-core kernels are NHWC: avoid per-conv transposes
+        # the sm_100a discriminator path (bf16 autocast) takes the reference's weight layout; only a
+        # cuDNN-run discriminator (fp32) profits from channels_last weights
+        self.d_channels_last = next(D.parameters()).is_cuda and not d_autocast
+        if self.d_channels_last:
             D.to(memory_format=torch.channels_last)
         self.eps_con = eps_con  # 1e-2 supervised, 1e-7 otherwise (t_cls_train.py:259-266)
         if distributed is None:
