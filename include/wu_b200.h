@@ -130,22 +130,20 @@ int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, 
 int wu_adain_apply(const void* x, const float* scale, const float* shift, void* out, int B, int HW,
                    int C, wu_stream_t stream);
 /* Backward, step 1: gz = adjoint(dropout o upsample)(gu) at low resolution, plus per-(b,c)
- * partial sums S1 = sum gz, S2 = sum gz * xhat (xhat = (x-mean)*rstd).  Separable: a horizontal
- * pass (applies the dropout mask) into `scratch` (bf16 [B][2h][w][C],
- * wu_adain_up_drop_bwd_scratch_bytes), then a vertical pass.
- *   gz bf16 [B][h][w][C]; partial fp32 [B][nchunk][C][2], nchunk = wu_adain_stats_chunks(h*w). */
-size_t wu_adain_up_drop_bwd_scratch_bytes(int B, int h, int w, int C);
+ * partial sums S1 = sum gz, S2 = sum gz * xhat (xhat = (x-mean)*rstd), in one pass over gu.
+ *   gz bf16 [B][h][w][C]; partial fp32 [B][nchunk][C][2], nchunk = wu_adain_bwd_chunks(h, w, C). */
+int wu_adain_bwd_chunks(int h, int w, int C);
 int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean, const float* rstd,
-                         void* gz, float* partial, void* scratch, int B, int h, int w, int C,
-                         float p_drop, const uint8_t* keep_bits, wu_stream_t stream);
-/* Backward, step 2: reduce the partials, emit k1 = S1/N and k2 = S2/(N-1) ([B][C] fp32), the apply
+                         void* gz, float* partial, int B, int h, int w, int C, float p_drop,
+                         const uint8_t* keep_bits, wu_stream_t stream);
+/* Backward, step 2: reduce the nchunk partials, emit k1 = S1/N and k2 = S2/(N-1) ([B][C] fp32), the apply
  * coefficients coef fp32 [3][B][C] (A = rstd*ystd, Bc = -A*k2*rstd, Cc = A*(k2*rstd*mean - k1)) and the
  * gradients of l1.weight / l1.bias (utils.py:31,46), overwritten: dlw [4C][nc], dlb [4C].
  * gh is caller scratch, fp32 [B][4C] (gradient of the style vector l1(cond)). */
 int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb, const float* partial,
-                       const float* ystd, const float* mean, const float* rstd, float* k1, float* k2,
-                       float* coef, float* gh, float* dlw, float* dlb, int B, int C, int nc, int HW,
-                       wu_stream_t stream);
+                       int nchunk, const float* ystd, const float* mean, const float* rstd, float* k1,
+                       float* k2, float* coef, float* gh, float* dlw, float* dlb, int B, int C, int nc,
+                       int HW, wu_stream_t stream);
 /* Backward, step 3: gx = relu'(x) * (A*gz + Bc*x + Cc)  ==  relu'(x) * rstd*ystd*(gz - k1 - xhat*k2),
  * bf16 [B][h][w][C]. */
 int wu_adain_bwd_apply(const void* gz, const void* x, const float* coef, void* gx, int B, int HW,

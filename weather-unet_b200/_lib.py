@@ -39,9 +39,9 @@ SIGNATURES = {
     "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "wu_adain_apply": (I, [P, P, P, P, I, I, I, P]),
     "wu_adain_up_drop_fwd": (I, [P, P, P, P, P, I, I, I, I, F, U64, P, I, P]),
-    "wu_adain_up_drop_bwd_scratch_bytes": (SZ, [I, I, I, I]),
-    "wu_adain_up_drop_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, P, P]),
-    "wu_adain_style_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
+    "wu_adain_bwd_chunks": (I, [I, I, I]),
+    "wu_adain_up_drop_bwd": (I, [P, P, P, P, P, P, I, I, I, I, F, P, P]),
+    "wu_adain_style_bwd": (I, [P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
     "wu_adain_bwd_apply": (I, [P, P, P, P, I, I, I, P]),
     "wu_bias_act_fwd": (I, [P, P, F, c_longlong, I, P]),
     "wu_bias_act_bwd_workspace_bytes": (SZ, [I]),

@@ -154,19 +154,18 @@ def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
     B, h, w, C = x.shape
     nc = cond.shape[1]
     dev = x.device
-    nchunk = query("wu_adain_stats_chunks", h * w)
+    nchunk = query("wu_adain_bwd_chunks", h, w, C)
     partial = torch.empty((B, nchunk, C, 2), dtype=torch.float32, device=dev)
     gz = torch.empty_like(x)
-    scratch = torch.empty((B, 2 * h, w, C), dtype=BF16, device=dev)
     call("wu_adain_up_drop_bwd", ptr(gu), ptr(x), ptr(st.mean), ptr(st.rstd), ptr(gz), ptr(partial),
-         ptr(scratch), B, h, w, C, st.p, ptr(st.bits), stream())
+         B, h, w, C, st.p, ptr(st.bits), stream())
     kk = torch.empty((5, B, C), dtype=torch.float32, device=dev)  # k1, k2, coef[3]
     gh = torch.empty((B, 4 * C), dtype=torch.float32, device=dev)
     dlw = torch.empty((4 * C, nc), dtype=torch.float32, device=dev)
     dlb = torch.empty((4 * C,), dtype=torch.float32, device=dev)
-    call("wu_adain_style_bwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.ystd), ptr(st.mean),
-         ptr(st.rstd), ptr(kk[0]), ptr(kk[1]), ptr(kk[2]), ptr(gh), ptr(dlw), ptr(dlb), B, C, nc, h * w,
-         stream())
+    call("wu_adain_style_bwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), nchunk, ptr(st.ystd),
+         ptr(st.mean), ptr(st.rstd), ptr(kk[0]), ptr(kk[1]), ptr(kk[2]), ptr(gh), ptr(dlw), ptr(dlb), B, C,
+         nc, h * w, stream())
     gx = torch.empty_like(x)
     call("wu_adain_bwd_apply", ptr(gz), ptr(x), ptr(kk[2]), ptr(gx), B, h * w, C, stream())
     return gx, dlw, dlb

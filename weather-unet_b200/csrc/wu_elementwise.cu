@@ -431,6 +431,18 @@ maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __rest
   }
 }
 // thread = (pooled pixel, 8 channels): writes the four full-resolution gradients of its window.
+// Everything stays in packed bf16x2: comparisons are 16-bit SIMD integer compares on an order-
+// preserving key (bf16 is sign-magnitude), the one addition is a bf16x2 add (exact sum, one rounding:
+// the same value an fp32 add + rounding gives).  A first version unpacked to fp32 (101 registers, 24 %
+// of the warps resident, latency bound at 48 % of HBM peak).
+__device__ __forceinline__ uint32_t bf16x2_order_key(uint32_t v) {
+  return v ^ (__vcmplts2(v, 0u) & 0x7FFF7FFFu);  // negative lanes: flip the magnitude bits
+}
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                   *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g_pool,
                     const __nv_bfloat16* __restrict__ g_skip, __nv_bfloat16* __restrict__ g, int B,
@@ -447,33 +459,35 @@ maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __
     const int b = (int)(t / Ho);
     const long long o00 = (((long long)b * H + 2 * ho) * W + 2 * wo) * C + v * 8;
     const long long offs[4] = {o00, o00 + C, o00 + (long long)W * C, o00 + (long long)W * C + C};
-    float yv[4][8], gs[4][8], gp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint4 yv[4], gs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      unpack8(ld_stream16(y + offs[k]), yv[k]);
-      if (g_skip != nullptr) {
-        unpack8(ld_stream16(g_skip + offs[k]), gs[k]);
-      } else {
+      yv[k] = ld_stream16(y + offs[k]);
+      gs[k] = g_skip != nullptr ? ld_stream16(g_skip + offs[k]) : make_uint4(0, 0, 0, 0);
+    }
+    const uint4 gp = g_pool != nullptr ? ld_stream16(g_pool + i * 8) : make_uint4(0, 0, 0, 0);
+    uint4 out[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gs[k][j] = 0.f;
+    for (int e = 0; e < 4; ++e) {  // two channels per 32-bit word
+      const uint32_t y0 = (&yv[0].x)[e], y1 = (&yv[1].x)[e], y2 = (&yv[2].x)[e], y3 = (&yv[3].x)[e];
+      const uint32_t k0 = bf16x2_order_key(y0), k1 = bf16x2_order_key(y1);
+      const uint32_t k2 = bf16x2_order_key(y2), k3 = bf16x2_order_key(y3);
+      // first maximum in window scan order (h-major), PyTorch's tie rule: a later element wins
+      // only when strictly greater
+      const uint32_t s01 = __vcmpgts2(k1, k0), s23 = __vcmpgts2(k3, k2);
+      const uint32_t m01 = __vmaxs2(k0, k1), m23 = __vmaxs2(k2, k3);
+      const uint32_t top = __vcmpgts2(m23, m01);  // the maximum is in the second row
+      const uint32_t is[4] = {~top & ~s01, ~top & s01, top & ~s23, top & s23};
+      const uint32_t gpe = (&gp.x)[e];
+      const uint32_t ys[4] = {y0, y1, y2, y3};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t sum = bf16x2_add((&gs[k].x)[e], gpe & is[k]);
+        (&out[k].x)[e] = sum & __vcmpgts2(ys[k], 0u);  // ReLU mask of y
       }
     }
-    if (g_pool != nullptr) unpack8(ld_stream16(g_pool + i * 8), gp);
-    float out[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // first maximum in window scan order (h-major), PyTorch's tie rule
-      int am = 0;
-      float mv = yv[0][j];
-#pragma unroll
-      for (int k = 1; k < 4; ++k)
-        if (yv[k][j] > mv) { mv = yv[k][j]; am = k; }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        out[k][j] = yv[k][j] > 0.f ? gs[k][j] + (k == am ? gp[j] : 0.f) : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) st_stream16(g + offs[k], pack8(out[k]));
+    for (int k = 0; k < 4; ++k) st_stream16(g + offs[k], out[k]);
   }
 }
 
@@ -693,108 +707,112 @@ __device__ __forceinline__ float bilinear_adjoint_w(int D, int s, float ratio, i
   return wgt;
 }
 
-// Adjoint of dropout o upsample, separable.  Pass 1 (horizontal, applies the dropout mask):
-//   t[b,Y,x,c] = sum_X wx(X->x) keep(b,Y,X,c)/(1-p) gu[b,Y,X,c],  X in [2x-2, 2x+3]
+// Adjoint of dropout o upsample, plus the per-(b, chunk, c) sums S1 = sum gz, S2 = sum gz * xhat, in
+// ONE pass over gu (a first version ran a horizontal pass into a scratch tensor and a vertical pass
+// out of it: 6.25 E + 4 E bytes moved for E = bytes of the low-resolution tensor, here 4.25 E + 2 E):
+//   gz[b,y,x,c] = sum_Y wy(Y->y) sum_X wx(X->x) keep(b,Y,X,c)/(1-p) gu[b,Y,X,c]
+// A block owns `groups` = 256 / (C/8) low-resolution columns x kAdjRows rows of one image; a thread
+// owns one (column, 8-channel vector) and walks DOWN the upsampled rows Y: the horizontally reduced row
+// t(Y) (six candidate X, four of them with non-zero weight) feeds the two output rows i0(Y), i0(Y)+1,
+// and because i0 never decreases two accumulators suffice: when i0 advances, the finished row is
+// written, added to the sums, and the accumulators shift.  i0(Y) is the same for the whole block.
 // keep comes from the byte tensor the forward pass stored (keep_bits == nullptr: no dropout).
-// grid = (ceil(w * C/8 / 256), B * ceil(2h / kRowsPerThread)); a thread handles kRowsPerThread rows.
+constexpr int kAdjRows = 16;
 __global__ void __launch_bounds__(256)
-adain_drop_hpass_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ t,
-                        const uint8_t* __restrict__ keep_bits, int h, int w, int C, float inv_keep) {
-  const int cv = C >> 3, Wo = 2 * w;
-  const int xi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (xi >= w * cv) return;
-  const int xx = xi / cv, v = xi - xx * cv;
-  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  float wx[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) wx[j] = bilinear_adjoint_w(2 * xx - 2 + j, xx, rw, w, Wo) * inv_keep;
-  const int Ho = 2 * h;
-  const int rows_per_img = (Ho + kRowsPerThread - 1) / kRowsPerThread;
-  const int b = blockIdx.y / rows_per_img;
-  const int Y0 = (blockIdx.y - b * rows_per_img) * kRowsPerThread;
-#pragma unroll
-  for (int i = 0; i < kRowsPerThread; ++i) {
-    if (Y0 + i >= Ho) break;
-    const long long rowi = (long long)b * Ho + Y0 + i;  // (b, Y) row index
-    const long long vbase = (rowi * Wo + 2 * xx - 2) * cv + v;
-    uint4 gv[6];
-    uint32_t kb[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      gv[j] = make_uint4(0, 0, 0, 0);
-      kb[j] = 0xFFu;
-      if (wx[j] != 0.f) {
-        gv[j] = ld_stream16(gu + (vbase + (long long)j * cv) * 8);
-        if (keep_bits != nullptr) kb[j] = __ldg(keep_bits + vbase + (long long)j * cv);
-      }
-    }
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      if (wx[j] != 0.f) {
-        const uint4 km = byte_to_lanes(kb[j]);
-        uint4 g = gv[j];
-        g.x &= km.x; g.y &= km.y; g.z &= km.z; g.w &= km.w;
-        float f[8];
-        unpack8(g, f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wx[j], f[e], acc[e]);
-      }
-    }
-    *reinterpret_cast<uint4*>(t + ((rowi * w + xx) * cv + v) * 8) = pack8(acc);
-  }
-}
-
-// Pass 2 (vertical) + per-(b,chunk,c) sums S1 = sum gz, S2 = sum gz * xhat:
-//   gz[b,y,x,c] = sum_Y wy(Y->y) t[b,Y,x,c],  Y in [2y-2, 2y+3]
-__global__ void __launch_bounds__(256)
-adain_up_vpass_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ x,
-                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                      __nv_bfloat16* __restrict__ gz, float* __restrict__ partial, int h, int w,
-                      int C, int nchunk) {
+adain_up_drop_adjoint_kernel(const __nv_bfloat16* __restrict__ gu, const uint8_t* __restrict__ keep_bits,
+                             const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                             const float* __restrict__ rstd, __nv_bfloat16* __restrict__ gz,
+                             float* __restrict__ partial, int h, int w, int C, float inv_keep,
+                             int col_blocks, int row_blocks) {
   extern __shared__ float red[];
   const int lanes = C >> 3, groups = blockDim.x / lanes;
   const int g = threadIdx.x / lanes, l = threadIdx.x % lanes;
-  const int b = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
-  const int HW = h * w, Ho = 2 * h;
+  const int chunks = col_blocks * row_blocks;
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int rb = chunk / col_blocks, cb = chunk - rb * col_blocks;
+  const int Ho = 2 * h, Wo = 2 * w;
+  const int y0 = rb * kAdjRows, y1 = min(h, y0 + kAdjRows);  // output rows [y0, y1)
+  const int xx = cb * groups + g;
+  const bool live = xx < w;
   const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
-  const int p0 = chunk * kStatChunk, p1 = min(HW, p0 + kStatChunk);
-  float mu[8], rs[8];
-  {
-    const float4* mp = reinterpret_cast<const float4*>(mean + (long long)b * C + l * 8);
-    const float4* rp = reinterpret_cast<const float4*>(rstd + (long long)b * C + l * 8);
-    const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), r0 = __ldg(rp), r1 = __ldg(rp + 1);
-    mu[0] = m0.x; mu[1] = m0.y; mu[2] = m0.z; mu[3] = m0.w;
-    mu[4] = m1.x; mu[5] = m1.y; mu[6] = m1.z; mu[7] = m1.w;
-    rs[0] = r0.x; rs[1] = r0.y; rs[2] = r0.z; rs[3] = r0.w;
-    rs[4] = r1.x; rs[5] = r1.y; rs[6] = r1.z; rs[7] = r1.w;
-  }
+  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  float wx[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    wx[j] = live ? bilinear_adjoint_w(2 * xx - 2 + j, xx, rw, w, Wo) * inv_keep : 0.f;
+  const float4* mp = reinterpret_cast<const float4*>(mean + (long long)b * C + l * 8);
+  const float4* rp = reinterpret_cast<const float4*>(rstd + (long long)b * C + l * 8);
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int p = p0 + g; p < p1; p += groups) {
-    const int yy = p / w, xx = p - yy * w;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int Y = 2 * yy - 2 + j;
-      const float wy = bilinear_adjoint_w(Y, yy, rh, h, Ho);
-      if (wy != 0.f) {
-        float f[8];
-        unpack8(ld_stream16(t + ((((long long)b * Ho + Y) * w + xx) * lanes + l) * 8), f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wy, f[e], acc[e]);
-      }
-    }
-    const long long off = ((long long)b * HW + p) * C + l * 8;
+  float accA[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accB[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int cur = y0 - 1;  // accA collects output row `cur`, accB row `cur + 1`
+  auto finish_row = [&](int r, const float (&acc)[8]) {
+    if (!live || r < y0 || r >= y1) return;
+    const long long off = (((long long)b * h + r) * w + xx) * C + l * 8;
     float xv[8];
     unpack8(ldg16(x + off), xv);
+    // mean / rstd are re-read (L1 hits) once per finished row instead of living in 16 registers
+    const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float rs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1[j] += acc[j];
-      s2[j] = fmaf(acc[j], (xv[j] - mu[j]) * rs[j], s2[j]);
+    for (int e = 0; e < 8; ++e) {
+      s1[e] += acc[e];
+      s2[e] = fmaf(acc[e], (xv[e] - mu[e]) * rs[e], s2[e]);
     }
     *reinterpret_cast<uint4*>(gz + off) = pack8(acc);
+  };
+  for (int Y = max(0, 2 * y0 - 3); Y < Ho; ++Y) {
+    int i0, i1;
+    float lam;
+    bilinear_src(Y, rh, h, i0, i1, lam);
+    if (i0 < y0 - 1) continue;  // feeds rows above this block only
+    if (i0 >= y1) break;        // rows [y0, y1) are complete
+    while (cur < i0) {          // block-uniform: row `cur` has all its contributions
+      finish_row(cur, accA);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        accA[e] = accB[e];
+        accB[e] = 0.f;
+      }
+      ++cur;
+    }
+    float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+      const long long vbase = (((long long)b * Ho + Y) * Wo + 2 * xx - 2) * lanes + l;
+      uint4 gv[6];
+      uint32_t kb[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        gv[j] = make_uint4(0, 0, 0, 0);
+        kb[j] = 0xFFu;
+        if (wx[j] != 0.f) {
+          gv[j] = ld_stream16(gu + (vbase + (long long)j * lanes) * 8);
+          if (keep_bits != nullptr) kb[j] = __ldg(keep_bits + vbase + (long long)j * lanes);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (wx[j] != 0.f) {
+          const uint4 km = byte_to_lanes(kb[j]);
+          uint4 gq = gv[j];
+          gq.x &= km.x; gq.y &= km.y; gq.z &= km.z; gq.w &= km.w;
+          float f[8];
+          unpack8(gq, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = fmaf(wx[j], f[e], t[e]);
+        }
+      }
+    }
+    const float wa = 1.f - lam, wb = (i1 != i0) ? lam : 0.f;  // i1 == i0 only on the last row (lam = 0)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      accA[e] = fmaf(wa, t[e], accA[e]);
+      accB[e] = fmaf(wb, t[e], accB[e]);
+    }
   }
-  block_reduce_pairs(red, s1, s2, C, lanes, g, l, partial + ((size_t)b * nchunk + chunk) * C * 2);
+  finish_row(cur, accA);
+  finish_row(cur + 1, accB);  // complete only when the loop ran out of rows (cur + 1 == h - 1 < y1)
+  block_reduce_pairs(red, s1, s2, C, lanes, g, l, partial + ((size_t)b * chunks + chunk) * C * 2);
 }
 
 // thread per (b, c): fold the partials, emit k1, k2 and the gradient of the 4 style numbers.
@@ -1087,49 +1105,45 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
   return WU_OK;
 }
-extern "C" size_t wu_adain_up_drop_bwd_scratch_bytes(int B, int h, int w, int C) {
-  if (B <= 0 || h <= 0 || w <= 0 || C <= 0) return 0;
-  return (size_t)B * 2 * h * w * C * sizeof(bf16);
+extern "C" int wu_adain_bwd_chunks(int h, int w, int C) {
+  if (h <= 0 || w <= 0 || C < 8 || C > 2048 || !pow2(C)) return 0;
+  const int groups = 256 / (C / 8);
+  return ((w + groups - 1) / groups) * ((h + kAdjRows - 1) / kAdjRows);
 }
 extern "C" int wu_adain_up_drop_bwd(const void* gu, const void* x, const float* mean,
-                                    const float* rstd, void* gz, float* partial, void* scratch,
-                                    int B, int h, int w, int C, float p_drop,
-                                    const uint8_t* keep_bits, wu_stream_t stream) {
-  WU_REQUIRE(gu && x && mean && rstd && gz && partial && scratch && B > 0 && h > 0 && w > 0,
+                                    const float* rstd, void* gz, float* partial, int B, int h, int w,
+                                    int C, float p_drop, const uint8_t* keep_bits,
+                                    wu_stream_t stream) {
+  WU_REQUIRE(gu && x && mean && rstd && gz && partial && B > 0 && h > 0 && w > 0,
              "wu_adain_up_drop_bwd: bad args");
   WU_REQUIRE_ADAIN_C("wu_adain_up_drop_bwd", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_bwd: p_drop=%f out of [0,1)", p_drop);
   WU_REQUIRE(p_drop == 0.f || keep_bits != nullptr,
              "wu_adain_up_drop_bwd: keep_bits (from the forward pass) is required when p_drop > 0");
-  const long long gy = (long long)B * ((2 * h + kRowsPerThread - 1) / kRowsPerThread);
-  WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_bwd: B*ceil(2h/4)=%lld exceeds 65535", gy);
-  const int nchunk = wu_adain_stats_chunks(h * w);
   const int lanes = C / 8, groups = 256 / lanes;
-  cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((w * (C / 8) + 255) / 256), (unsigned)gy);
-  adain_drop_hpass_kernel<<<grid, 256, 0, st>>>((const bf16*)gu, (bf16*)scratch,
-                                                p_drop > 0.f ? keep_bits : nullptr, h, w, C,
-                                                1.f / (1.f - p_drop));
-  WU_CHECK_LAUNCH("adain_drop_hpass_kernel");
-  adain_up_vpass_kernel<<<B * nchunk, 256, 2 * groups * C * sizeof(float), st>>>(
-      (const bf16*)scratch, (const bf16*)x, mean, rstd, (bf16*)gz, partial, h, w, C, nchunk);
-  WU_CHECK_LAUNCH("adain_up_vpass_kernel");
+  const int col_blocks = (w + groups - 1) / groups, row_blocks = (h + kAdjRows - 1) / kAdjRows;
+  const long long blocks = (long long)B * col_blocks * row_blocks;
+  WU_REQUIRE(blocks < (1LL << 31), "wu_adain_up_drop_bwd: too many blocks");
+  adain_up_drop_adjoint_kernel<<<(unsigned)blocks, 256, 2 * groups * C * sizeof(float),
+                                 (cudaStream_t)stream>>>(
+      (const bf16*)gu, p_drop > 0.f ? keep_bits : nullptr, (const bf16*)x, mean, rstd, (bf16*)gz, partial,
+      h, w, C, 1.f / (1.f - p_drop), col_blocks, row_blocks);
+  WU_CHECK_LAUNCH("adain_up_drop_adjoint_kernel");
   return WU_OK;
 }
 extern "C" int wu_adain_style_bwd(const float* cond, const float* lw, const float* lb,
-                                  const float* partial, const float* ystd, const float* mean,
-                                  const float* rstd, float* k1, float* k2, float* coef, float* gh,
-                                  float* dlw, float* dlb, int B, int C, int nc, int HW,
-                                  wu_stream_t stream) {
+                                  const float* partial, int nchunk, const float* ystd,
+                                  const float* mean, const float* rstd, float* k1, float* k2,
+                                  float* coef, float* gh, float* dlw, float* dlb, int B, int C, int nc,
+                                  int HW, wu_stream_t stream) {
   WU_REQUIRE(cond && lw && lb && partial && ystd && mean && rstd && k1 && k2 && coef && gh && dlw &&
                  dlb,
              "wu_adain_style_bwd: null pointer");
-  WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0, "wu_adain_style_bwd: bad shape");
+  WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0 && nchunk > 0, "wu_adain_style_bwd: bad shape");
   WU_REQUIRE((B * C) % 4 == 0, "wu_adain_style_bwd: B*C=%d must be a multiple of 4", B * C);
   cudaStream_t st = (cudaStream_t)stream;
   adain_style_bwd_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(cond, lw, lb, partial, ystd, mean, rstd,
-                                                              k1, k2, coef, gh, B, C, nc, HW,
-                                                              wu_adain_stats_chunks(HW));
+                                                              k1, k2, coef, gh, B, C, nc, HW, nchunk);
   WU_CHECK_LAUNCH("adain_style_bwd_kernel");
   adain_style_bwd_params_kernel<<<(4 * C + 127) / 128, 128, 0, st>>>(gh, cond, dlw, dlb, B, 4 * C, nc);
   WU_CHECK_LAUNCH("adain_style_bwd_params_kernel");

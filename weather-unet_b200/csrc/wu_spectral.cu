@@ -27,7 +27,7 @@ struct SnTensor {   // one record of the device-side table (13 x 8 bytes)
   float* sigma;     // [1]
   float* t;         // [cols] scratch: W^T u
   float* s;         // [rows] scratch: W v
-  float* part;      // [kSnParts] scratch: partial sums of squares / dots
+  float* part;      // [2 * kSnParts] scratch: partial sums of squares / dots
   float* w_sn;      // [rows][cols] W / sigma
   const float* g;   // backward: gradient w.r.t. w_sn
   float* dw;        // backward: gradient w.r.t. w
@@ -39,8 +39,8 @@ struct SnChunk {  // work item
   int count;
   int index;      // index of this chunk within its tensor (sn_bwd records: number of sn_dot chunks)
 };
-constexpr int kSnParts = 64;  // partial slots per tensor per reduction
-constexpr int kSnCols = 128;  // columns per sn_wtu chunk
+constexpr int kSnParts = 128;  // partial slots per tensor per reduction
+constexpr int kSnCols = 32;    // columns per sn_wtu chunk
 constexpr int kSnRows = 8;    // rows per sn_wv chunk
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -60,28 +60,38 @@ __device__ __forceinline__ float block_sum(float v, float* red /* [8] */) {
   return s;
 }
 
-// t[c] = sum_r W[r][c] u[r] for 128 columns; part[index] = sum over these columns of t^2
+// t[c] = sum_r W[r][c] u[r] for 32 columns (8 row groups per block, one warp = 128 contiguous bytes
+// of a row); part[index] = sum over these columns of t^2
 __global__ void __launch_bounds__(256)
 sn_wtu_kernel(const SnTensor* __restrict__ tensors, const SnChunk* __restrict__ chunks) {
-  __shared__ float half[kSnCols];
-  __shared__ float red[8];
+  __shared__ float grp[8][kSnCols];
   const SnChunk ck = chunks[blockIdx.x];
   const SnTensor T = tensors[ck.t];
-  const int c = ck.begin + (threadIdx.x & (kSnCols - 1));
-  const int r0 = threadIdx.x >> 7;  // 0 / 1: even / odd rows
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = ck.begin + lane;
   float acc = 0.f;
-  if (c < T.cols)
-    for (int r = r0; r < T.rows; r += 2) acc = fmaf(T.w[(size_t)r * T.cols + c], T.u[r], acc);
-  if (r0 == 1) half[threadIdx.x & (kSnCols - 1)] = acc;
-  __syncthreads();
-  float sq = 0.f;
-  if (r0 == 0 && c < T.cols) {
-    acc += half[threadIdx.x];
-    T.t[c] = acc;
-    sq = acc * acc;
+  if (c < T.cols) {
+    int r = g;
+    for (; r + 24 < T.rows; r += 32) {  // four independent loads in flight
+      const float a0 = T.w[(size_t)r * T.cols + c], a1 = T.w[(size_t)(r + 8) * T.cols + c];
+      const float a2 = T.w[(size_t)(r + 16) * T.cols + c], a3 = T.w[(size_t)(r + 24) * T.cols + c];
+      acc = fmaf(a0, T.u[r], acc);
+      acc = fmaf(a1, T.u[r + 8], acc);
+      acc = fmaf(a2, T.u[r + 16], acc);
+      acc = fmaf(a3, T.u[r + 24], acc);
+    }
+    for (; r < T.rows; r += 8) acc = fmaf(T.w[(size_t)r * T.cols + c], T.u[r], acc);
   }
-  const float tot = block_sum(sq, red);
-  if (threadIdx.x == 0) T.part[ck.index] = tot;
+  grp[g][lane] = acc;
+  __syncthreads();
+  if (g == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += grp[i][lane];
+    if (c < T.cols) T.t[c] = tot;
+    const float sq = warp_sum(c < T.cols ? tot * tot : 0.f);
+    if (lane == 0) T.part[ck.index] = sq;
+  }
 }
 
 // training: v = t / max(||t||, eps) (this chunk writes its share of v), s[r] = W[r] . v for 8 rows;
@@ -123,7 +133,7 @@ sn_wv_kernel(const SnTensor* __restrict__ tensors, const SnChunk* __restrict__ c
     acc = warp_sum(acc) * inv;
     if (lane == 0) T.s[r] = acc;
   }
-  // part slots kSnParts/2.. hold the partial ||s||^2 (the lower half holds ||t||^2 partials)
+  // part slots kSnParts.. hold the partial ||s||^2 (the first kSnParts hold ||t||^2 / dot partials)
   const float sq = (lane == 0 && r < T.rows) ? acc * acc : 0.f;
   const float tot = block_sum(sq, red);
   if (threadIdx.x == 0) T.part[kSnParts + ck.index] = tot;
