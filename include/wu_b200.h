@@ -177,7 +177,9 @@ int wu_conv3to64_s2_wgrad(const float* h1, const void* g, float* dw, float* db, 
 size_t wu_conv3to64_s2_dgrad_workspace_bytes(void);
 int wu_conv3to64_s2_dgrad(const void* g, const float* w, float* g_h1, int B, int Hin, int Win,
                           void* workspace, size_t workspace_bytes, wu_stream_t stream);
-/* Backward of the 3->3 convolution: g_x fp32 NCHW (may be NULL), dw [3][3][3][3], db [3] (may be NULL). */
+/* Backward of the 3->3 convolution: g_x fp32 NCHW (may be NULL: real images / detached fakes need
+ * none), dw [3][3][3][3] (may be NULL: the generator update discards the discriminator's weight
+ * gradients), db [3] (may be NULL); workspace is only needed with dw. */
 size_t wu_conv3to3_bprop_workspace_bytes(void);
 int wu_conv3to3_bprop(const float* g_h1, const float* x, const float* w, float* g_x, float* dw,
                       float* db, int B, int H, int W, void* workspace, size_t workspace_bytes,

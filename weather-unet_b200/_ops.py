@@ -263,8 +263,9 @@ class _DiscStem(torch.autograd.Function):
             nb = query("wu_conv3to3_bprop_workspace_bytes")
             ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
             gx = torch.empty_like(x) if need_x else None
-            dw0 = torch.empty((3, 3, 3, 3), dtype=torch.float32, device=dev)
-            db0 = torch.empty((3,), dtype=torch.float32, device=dev)
+            if need_w0 or need_b0:
+                dw0 = torch.empty((3, 3, 3, 3), dtype=torch.float32, device=dev)
+                db0 = torch.empty((3,), dtype=torch.float32, device=dev)
             call("wu_conv3to3_bprop", ptr(gh), ptr(x), ptr(w0c), ptr(gx), ptr(dw0), ptr(db0), B, H, W,
                  ptr(ws), nb, stream())
         return (gx, dw0 if need_w0 else None, db0 if need_b0 else None, dw1,

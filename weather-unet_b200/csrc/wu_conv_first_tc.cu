@@ -332,4 +332,265 @@ int conv_k27_fprop_tc(const float* x, const float* w, const float* bias, float s
   return stride == 2 ? launch_k27<2, false>(xm, dm, p, st) : launch_k27<1, false>(xm, dm, p, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight + bias gradient of the same layers:  dw[co][k] = sum_px dY[px][co] * patch[px][k]
+// ------------------------------------------------------------------------------------------------
+// As an FMA kernel this was instruction bound (0.68 ms for 64 x 256 x 256 pixels; reading dY takes
+// 0.09 ms of HBM time).  On tcgen05: GEMM-K = pixels (64 per tile), A = patch rows P[px][128] bf16
+// (MN-major; columns 0..26 = bf16(x), 27 = 1 for the bias gradient, 32..58 = bf16(x - bf16(x)) so that
+// hi + lo carries 16 significant bits of the fp32 image, 64..127 a shared all-zero atom), B = the dY
+// tile [64 px][64 co] as TMA delivers it (MN-major).  One accumulator D[128][64] per CTA lives in TMEM
+// for the whole kernel; the per-CTA results are folded by a second small kernel:
+//   dw[co][k] = sum_cta D[k][co] + D[32 + k][co],   db[co] = sum_cta D[27][co].
+// Warp roles: 0 = TMA (raw image boxes + dY tiles), 1-2 = patch rows, 3 = MMA issuer; warps 0-1 read
+// the accumulator back at the end (TMEM lanes 0..63).
+struct K27WgradParams {
+  int bw, bh, log2_bw, bx, by;
+  int tiles_w, tiles_h, num_tiles;
+  float* partial;  // [gridDim.x][64 rows n][64 co]
+};
+constexpr int kW27Stages = 4;
+constexpr int kW27RawBytes = 10240;
+constexpr int kW27AtomBytes = 64 * 128;  // 64 pixels x 64 bf16
+constexpr int kW27StageBytes = kW27RawBytes + 2 * kW27AtomBytes;  // raw box | dY tile | patch rows
+constexpr int kW27Smem = kW27Stages * kW27StageBytes + kW27AtomBytes + 1024 + 1024;
+
+template <int STRIDE>
+__global__ void __launch_bounds__(128, 1)
+conv_k27_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                      const K27WgradParams p) {
+  constexpr int S = kW27Stages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  auto raw_addr = [&](int s) { return base + s * kW27StageBytes; };
+  auto dy_addr = [&](int s) { return base + s * kW27StageBytes + kW27RawBytes; };
+  auto p_addr = [&](int s) { return base + s * kW27StageBytes + kW27RawBytes + kW27AtomBytes; };
+  const uint32_t zero_base = base + S * kW27StageBytes;
+  const uint32_t bar_base = zero_base + kW27AtomBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  const uint32_t done_bar = bar_base + 8u * (3 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 3 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(pfull_bar(s), 64);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < kW27AtomBytes / 16; i += blockDim.x)  // the shared all-zero atom
+    *reinterpret_cast<uint4*>(smem + (zero_base - base) + i * 16) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int tile, int& b, int& h0, int& w0) {
+    const int tw = tile % p.tiles_w;
+    const int t2 = tile / p.tiles_w;
+    const int th = t2 % p.tiles_h;
+    b = t2 / p.tiles_h;
+    h0 = th * p.bh;
+    w0 = tw * p.bw;
+  };
+  const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(p.bx * p.by * 3 * 4) + kW27AtomBytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int b, h0, w0;
+        decode(tile, b, h0, w0);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), bytes);
+        tma_load_4d(raw_addr(stage), &tmX, full_bar(stage), w0 * STRIDE - 4, h0 * STRIDE - 1, 0, b);
+        tma_load_4d(dy_addr(stage), &tmY, full_bar(stage), 0, w0, h0, b);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp < 3) {
+    // ------------------------------------------------------------------ patch rows (one pixel each)
+    const int row = threadIdx.x - 32;  // 0..63
+    const int ph = row >> p.log2_bw, pw = row & (p.bw - 1);
+    const int cstride = p.bx * p.by;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      mbar_wait(full_bar(stage), phase);
+      const float* r0 = reinterpret_cast<const float*>(smem + (raw_addr(stage) - base)) +
+                        (ph * STRIDE) * p.bx + pw * STRIDE + 3;
+      uint32_t hi[16], lo[16];  // 32 bf16 each: k = ci*9 + r*3 + s, slot 27 of hi = 1.0
+      float v[32];
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) v[ci * 9 + r * 3 + s] = r0[ci * cstride + r * p.bx + s];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = v[2 * j], c = v[2 * j + 1];
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), ch = __float2bfloat16_rn(c);
+        hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(ch) << 16);
+        lo[j] = pack_bf16x2(a - __bfloat162float(ah), c - __bfloat162float(ch));
+      }
+      hi[13] = (hi[13] & 0x0000FFFFu) | 0x3F800000u;  // slot 27 (upper half of word 13) = bf16(1.0)
+      uint8_t* prow = smem + (p_addr(stage) - base) + row * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
+            make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(prow + (((c + 4) ^ (row & 7)) << 4)) =
+            make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(pfull_bar(stage));
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else {
+    if (lane == 0) {
+      // -------------------------------------------------------------- MMA issuer (one thread)
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(full_bar(stage), phase);   // dY tile landed (async proxy)
+        mbar_wait(pfull_bar(stage), phase);  // patch rows written
+        tc_fence_after();
+        // A: atom 0 = patch rows of this stage, atom 1 = the shared zero atom (LBO = their distance)
+        const uint32_t pa = p_addr(stage);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 pixels = 2048 bytes)
+          const uint64_t adesc = umma_smem_desc_sw128(pa + k * 2048, zero_base - pa, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(dy_addr(stage) + k * 2048, kW27AtomBytes, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  }
+  if (warp < 2) {
+    // accumulator rows n = TMEM lanes 0..63 -> partial[cta][n][co]
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    uint32_t v[64];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+    tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+    tmem_ld_wait();
+    float4* o = reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.x * 64 + warp * 32 + lane) * 64);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      o[j] = my_tiles > 0 ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem_base);
+}
+
+// dw[co][k] = sum_cta D[k][co] + D[32+k][co] (k < 27), db[co] = sum_cta D[27][co]
+__global__ void conv_k27_wgrad_fold_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                           float* __restrict__ db, int nblocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // k * 64 + co
+  if (i >= 28 * 64) return;
+  const int k = i >> 6, co = i & 63;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) {
+    const float* d = partial + (size_t)b * 4096;
+    s += d[k * 64 + co];
+    if (k < 27) s += d[(32 + k) * 64 + co];
+  }
+  if (k < 27) dw[co * 27 + k] = s;
+  else if (db != nullptr) db[co] = s;
+}
+
+static void k27_wgrad_geometry(int Ho, int Wo, int stride, K27WgradParams* p) {
+  long best = -1;
+  for (int bw = 64; bw >= 8; bw >>= 1) {
+    const int bh = 64 / bw;
+    const long padded = (long)((Wo + bw - 1) / bw) * bw * (long)((Ho + bh - 1) / bh) * bh;
+    if (best < 0 || padded < best) {
+      best = padded;
+      p->bw = bw;
+      p->bh = bh;
+    }
+  }
+  p->log2_bw = 0;
+  while ((1 << p->log2_bw) < p->bw) ++p->log2_bw;
+  p->bx = p->bw * stride + 8;
+  p->by = (p->bh - 1) * stride + 3;
+  p->tiles_w = (Wo + p->bw - 1) / p->bw;
+  p->tiles_h = (Ho + p->bh - 1) / p->bh;
+}
+
+bool conv_k27_wgrad_tc_supported(const float* x, int Win) {
+  return Win % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+size_t conv_k27_wgrad_tc_workspace_bytes() { return (size_t)num_sms() * 4096 * sizeof(float); }
+
+int conv_k27_wgrad_tc(const float* x, const void* dy, float* dw, float* db, int B, int Hin, int Win,
+                      int stride, void* workspace, cudaStream_t st) {
+  const int Ho = stride == 2 ? (Hin + 1) / 2 : Hin, Wo = stride == 2 ? (Win + 1) / 2 : Win;
+  K27WgradParams p;
+  k27_wgrad_geometry(Ho, Wo, stride, &p);
+  WU_REQUIRE(p.bx * p.by * 12 <= kW27RawBytes, "first-layer wgrad: raw box %dx%d too large", p.bx, p.by);
+  const long long nt = (long long)B * p.tiles_w * p.tiles_h;
+  WU_REQUIRE(nt > 0 && nt < (1LL << 31), "first-layer wgrad: too many tiles");
+  p.num_tiles = (int)nt;
+  p.partial = reinterpret_cast<float*>(workspace);
+  CUtensorMap xm, ym;
+  int rc;
+  if ((rc = make_image_tmap(&xm, x, B, 3, Hin, Win, p.bx, p.by)) != WU_OK) return rc;
+  if ((rc = make_act_tmap(&ym, dy, B, Ho, Wo, 64, 64, p.bw, p.bh)) != WU_OK) return rc;
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv_k27_wgrad_kernel<1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kW27Smem));
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv_k27_wgrad_kernel<2>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kW27Smem));
+    attr_done = true;
+  }
+  const int grid = num_sms();
+  if (stride == 2) conv_k27_wgrad_kernel<2><<<grid, 128, kW27Smem, st>>>(xm, ym, p);
+  else conv_k27_wgrad_kernel<1><<<grid, 128, kW27Smem, st>>>(xm, ym, p);
+  WU_CHECK_LAUNCH("conv_k27_wgrad_kernel");
+  conv_k27_wgrad_fold_kernel<<<7, 256, 0, st>>>(p.partial, dw, db, grid);
+  WU_CHECK_LAUNCH("conv_k27_wgrad_fold_kernel");
+  return WU_OK;
+}
+
 }  // namespace wu

@@ -973,25 +973,32 @@ static int first_wgrad_blocks(long long npix) {
   if (g > tiles) g = tiles;
   return (int)(g < 1 ? 1 : g);
 }
+static size_t first_wgrad_ws(long long npix) {
+  const size_t fma = (size_t)first_wgrad_blocks(npix) * 2048 * sizeof(float);
+  const size_t tc = conv_k27_wgrad_tc_workspace_bytes();
+  return fma > tc ? fma : tc;
+}
 extern "C" size_t wu_conv_first_wgrad_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return (size_t)first_wgrad_blocks((long long)B * H * W) * 2048 * sizeof(float);
+  return first_wgrad_ws((long long)B * H * W);
 }
 extern "C" int wu_conv_first_wgrad(const float* x, const void* dy, float* dw, float* db, int B,
                                    int H, int W, void* workspace, size_t workspace_bytes,
                                    wu_stream_t stream) {
   WU_REQUIRE(x && dy && dw && workspace && B > 0 && H > 0 && W > 0, "wu_conv_first_wgrad: bad args");
-  const int blocks = first_wgrad_blocks((long long)B * H * W);
-  WU_REQUIRE(workspace_bytes >= (size_t)blocks * 2048 * sizeof(float),
+  WU_REQUIRE(workspace_bytes >= first_wgrad_ws((long long)B * H * W),
              "wu_conv_first_wgrad: workspace %zu too small", workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
+  if (conv_k27_wgrad_tc_supported(x, W))  // tcgen05 path (wu_conv_first_tc.cu)
+    return conv_k27_wgrad_tc(x, dy, dw, db, B, H, W, 1, workspace, st);
+  // image rows not 16-byte aligned (TMA cannot fetch them): FMA kernel
+  const int blocks = first_wgrad_blocks((long long)B * H * W);
   conv_first_wgrad_kernel<1><<<blocks, 256, 0, st>>>(x, (const bf16*)dy, (float*)workspace, B, H, W);
   WU_CHECK_LAUNCH("conv_first_wgrad_kernel");
   conv_first_wgrad_final_kernel<<<8, 256, 0, st>>>((const float*)workspace, dw, db, blocks);
   WU_CHECK_LAUNCH("conv_first_wgrad_final_kernel");
   return WU_OK;
 }
-
 extern "C" int wu_conv_last_tanh_fprop(const void* x, const float* w, const float* bias, float* y,
                                        int B, int H, int W, wu_stream_t stream) {
   WU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "wu_conv_last_tanh_fprop: bad args");
@@ -1180,7 +1187,7 @@ extern "C" int wu_conv3to64_s2_fprop(const float* h1, const float* w, const floa
 }
 extern "C" size_t wu_conv3to64_s2_wgrad_workspace_bytes(int B, int Hin, int Win) {
   if (B <= 0 || Hin <= 0 || Win <= 0) return 0;
-  return (size_t)first_wgrad_blocks((long long)B * (Hin / 2) * (Win / 2)) * 2048 * sizeof(float);
+  return first_wgrad_ws((long long)B * (Hin / 2) * (Win / 2));
 }
 extern "C" int wu_conv3to64_s2_wgrad(const float* h1, const void* g, float* dw, float* db, int B,
                                      int Hin, int Win, void* workspace, size_t workspace_bytes,
@@ -1189,10 +1196,12 @@ extern "C" int wu_conv3to64_s2_wgrad(const float* h1, const void* g, float* dw, 
              "wu_conv3to64_s2_wgrad: bad args");
   WU_REQUIRE(Hin % 2 == 0 && Win % 2 == 0, "wu_conv3to64_s2_wgrad: need even Hin, Win");
   const int H = Hin / 2, W = Win / 2;
-  const int blocks = first_wgrad_blocks((long long)B * H * W);
-  WU_REQUIRE(workspace_bytes >= (size_t)blocks * 2048 * sizeof(float),
+  WU_REQUIRE(workspace_bytes >= first_wgrad_ws((long long)B * H * W),
              "wu_conv3to64_s2_wgrad: workspace %zu too small", workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
+  if (conv_k27_wgrad_tc_supported(h1, Win))
+    return conv_k27_wgrad_tc(h1, g, dw, db, B, Hin, Win, 2, workspace, st);
+  const int blocks = first_wgrad_blocks((long long)B * H * W);
   conv_first_wgrad_kernel<2><<<blocks, 256, 0, st>>>(h1, (const bf16*)g, (float*)workspace, B, H, W);
   WU_CHECK_LAUNCH("conv_first_wgrad_kernel<2>");
   conv_first_wgrad_final_kernel<<<8, 256, 0, st>>>((const float*)workspace, dw, db, blocks);

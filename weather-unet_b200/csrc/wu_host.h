@@ -62,6 +62,13 @@ int wgrad_fold(const float* partial, int splits, int cin, int cout, float* dw, c
 int conv_k27_fprop_tc(const float* x, const float* w, const float* bias, float slope, void* dst, int B,
                       int Hin, int Win, int stride, cudaStream_t st);
 
+// Weight / bias gradient of the same layers on tcgen05 (image row pitch must be a multiple of 16 bytes:
+// conv_k27_wgrad_tc_supported); workspace = conv_k27_wgrad_tc_workspace_bytes().
+bool conv_k27_wgrad_tc_supported(const float* x, int Win);
+size_t conv_k27_wgrad_tc_workspace_bytes();
+int conv_k27_wgrad_tc(const float* x, const void* dy, float* dw, float* db, int B, int Hin, int Win,
+                      int stride, void* workspace, cudaStream_t st);
+
 // Launch accounting behind wu_launch_count().
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }

@@ -101,100 +101,126 @@ bias_act_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__
 //   -> c1 = LeakyReLU(Conv2d(3,64,3,padding=1,stride=2)(h1))   (NHWC bf16, wu_conv3to64_s2_*)
 // Three-channel tensors are FMA / HBM work, not tensor-core work (K = 27).
 // ------------------------------------------------------------------------------------------------
+// One thread = a strip of 4 consecutive output pixels of a row: the 3 x 3 x 6 input values of the
+// strip are loaded once and reused by the 4 pixels, and each of the 81 weights is read from shared
+// memory once per strip (a first version, one pixel per thread, re-read all 81 per pixel and was
+// bound by shared-memory loads: 100 us for 100 MB of traffic).
+// FLIP: use w'[ci][co][r][s] = w[co][ci][2-r][2-s], i.e. the transposed convolution = data gradient.
+template <bool FLIP>
 __global__ void __launch_bounds__(256)
-conv3to3_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+conv3to3_strip_kernel(const float* __restrict__ x, const float* __restrict__ w,
                       const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W) {
-  __shared__ float ws[81];
+  __shared__ float ws[81];  // [co][ci][r][s] of the convolution actually applied
   __shared__ float bs[3];
-  if (threadIdx.x < 81) ws[threadIdx.x] = w[threadIdx.x];
+  if (threadIdx.x < 81) {
+    const int co = threadIdx.x / 27, rem = threadIdx.x % 27, ci = rem / 9, t = rem % 9;
+    ws[threadIdx.x] = FLIP ? w[ci * 27 + co * 9 + (8 - t)] : w[threadIdx.x];
+  }
   if (threadIdx.x < 3) bs[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
   __syncthreads();
-  const long long HW = (long long)H * W, npix = (long long)B * HW;
-  for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
-       px += (long long)gridDim.x * blockDim.x) {
-    const int wq = (int)(px % W);
-    const long long t = px / W;
+  const int W4 = (W + 3) >> 2;
+  const long long HW = (long long)H * W, nstrips = (long long)B * H * W4;
+  const bool vec = (W & 3) == 0;
+  for (long long st = blockIdx.x * (long long)blockDim.x + threadIdx.x; st < nstrips;
+       st += (long long)gridDim.x * blockDim.x) {
+    const int w0 = (int)(st % W4) * 4;
+    const long long t = st / W4;
     const int hq = (int)(t % H);
     const long long b = t / H;
-    float acc[3] = {bs[0], bs[1], bs[2]};
+    float acc[3][4];
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[co][p] = bs[co];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r) {
+        const int hh = hq + r - 1;
+        if (hh < 0 || hh >= H) continue;
+        const float* row = x + (b * 3 + ci) * HW + (long long)hh * W;
+        float v[6];
 #pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) {
-          const int hh = hq + r - 1, ww = wq + s3 - 1;
-          const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                              ? __ldg(x + (b * 3 + ci) * HW + (long long)hh * W + ww)
-                              : 0.f;
-#pragma unroll
-          for (int co = 0; co < 3; ++co) acc[co] = fmaf(v, ws[co * 27 + ci * 9 + r * 3 + s3], acc[co]);
+        for (int c = 0; c < 6; ++c) {
+          const int ww = w0 + c - 1;
+          v[c] = (ww >= 0 && ww < W) ? __ldg(row + ww) : 0.f;
         }
 #pragma unroll
-    for (int co = 0; co < 3; ++co) y[(b * 3 + co) * HW + (long long)hq * W + wq] = acc[co];
+        for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+          for (int co = 0; co < 3; ++co) {
+            const float wv = ws[co * 27 + ci * 9 + r * 3 + s3];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[co][p] = fmaf(v[p + s3], wv, acc[co][p]);
+          }
+      }
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      float* o = y + (b * 3 + co) * HW + (long long)hq * W + w0;
+      if (vec) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[co][0], acc[co][1], acc[co][2], acc[co][3]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (w0 + p < W) o[p] = acc[co][p];
+      }
+    }
   }
 }
 
-// Backward of Conv2d(3,3,3,padding=1): g_x = conv_transpose(g_h1, w0) (optional), and per-block
-// partial sums of dw0[co][ci][r][s] = sum g_h1[co] * x[ci][shifted], db0[co] = sum g_h1[co].
-constexpr int kStemBwdBlocks = 148 * 8;
+// Weight / bias gradient of Conv2d(3,3,3,padding=1): per-block partial sums of
+// dw0[co][ci][r][s] = sum g_h1[co] * x[ci][shifted], db0[co] = sum g_h1[co]; same 4-pixel strips,
+// 84 accumulators per thread.
+constexpr int kStemBwdBlocks = 148 * 2;
 __global__ void __launch_bounds__(256)
-conv3to3_bprop_kernel(const float* __restrict__ gh, const float* __restrict__ x,
-                      const float* __restrict__ w, float* __restrict__ gx,
+conv3to3_wgrad_kernel(const float* __restrict__ gh, const float* __restrict__ x,
                       float* __restrict__ partial, int B, int H, int W) {
-  __shared__ float ws[81];
   __shared__ float red[8][84];
-  if (threadIdx.x < 81) ws[threadIdx.x] = w[threadIdx.x];
-  __syncthreads();
-  const long long HW = (long long)H * W, npix = (long long)B * HW;
+  const int W4 = (W + 3) >> 2;
+  const long long HW = (long long)H * W, nstrips = (long long)B * H * W4;
   float dw[81];
   float db[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 81; ++i) dw[i] = 0.f;
-  for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
-       px += (long long)gridDim.x * blockDim.x) {
-    const int wq = (int)(px % W);
-    const long long t = px / W;
+  for (long long st = blockIdx.x * (long long)blockDim.x + threadIdx.x; st < nstrips;
+       st += (long long)gridDim.x * blockDim.x) {
+    const int w0 = (int)(st % W4) * 4;
+    const long long t = st / W4;
     const int hq = (int)(t % H);
     const long long b = t / H;
-    const long long off = (long long)hq * W + wq;
-    const float g0 = gh[(b * 3 + 0) * HW + off], g1 = gh[(b * 3 + 1) * HW + off],
-                g2 = gh[(b * 3 + 2) * HW + off];
-    db[0] += g0; db[1] += g1; db[2] += g2;
-    float gxa[3] = {0.f, 0.f, 0.f};
+    float gv[3][4];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int co = 0; co < 3; ++co) {
+      const float* grow = gh + (b * 3 + co) * HW + (long long)hq * W + w0;
 #pragma unroll
-      for (int s3 = 0; s3 < 3; ++s3) {
-        // weight gradient: x at (h+r-1, w+s-1)
-        const int hh = hq + r - 1, ww = wq + s3 - 1;
-        const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float xv = in ? __ldg(x + (b * 3 + ci) * HW + (long long)hh * W + ww) : 0.f;
-          dw[0 * 27 + ci * 9 + r * 3 + s3] = fmaf(g0, xv, dw[0 * 27 + ci * 9 + r * 3 + s3]);
-          dw[1 * 27 + ci * 9 + r * 3 + s3] = fmaf(g1, xv, dw[1 * 27 + ci * 9 + r * 3 + s3]);
-          dw[2 * 27 + ci * 9 + r * 3 + s3] = fmaf(g2, xv, dw[2 * 27 + ci * 9 + r * 3 + s3]);
-        }
-        // data gradient: g_h1 at (h+1-r, w+1-s)
-        if (gx != nullptr) {
-          const int h2 = hq + 1 - r, w2 = wq + 1 - s3;
-          if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) {
-            const long long o2 = (long long)h2 * W + w2;
-#pragma unroll
-            for (int co = 0; co < 3; ++co) {
-              const float gv = __ldg(gh + (b * 3 + co) * HW + o2);
-#pragma unroll
-              for (int ci = 0; ci < 3; ++ci)
-                gxa[ci] = fmaf(gv, ws[co * 27 + ci * 9 + r * 3 + s3], gxa[ci]);
-            }
-          }
-        }
+      for (int p = 0; p < 4; ++p) {
+        gv[co][p] = (w0 + p < W) ? __ldg(grow + p) : 0.f;
+        db[co] += gv[co][p];
       }
-    if (gx != nullptr) {
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) gx[(b * 3 + ci) * HW + off] = gxa[ci];
     }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = hq + r - 1;
+        if (hh < 0 || hh >= H) continue;
+        const float* row = x + (b * 3 + ci) * HW + (long long)hh * W;
+        float v[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const int ww = w0 + c - 1;
+          v[c] = (ww >= 0 && ww < W) ? __ldg(row + ww) : 0.f;
+        }
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+          for (int co = 0; co < 3; ++co) {
+            float a = dw[co * 27 + ci * 9 + r * 3 + s3];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a = fmaf(gv[co][p], v[p + s3], a);
+            dw[co * 27 + ci * 9 + r * 3 + s3] = a;
+          }
+      }
   }
   // block reduction of the 84 partial sums: warp shuffles, then 8 warps through shared memory
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -268,14 +294,18 @@ extern "C" int wu_bias_act_bwd(const void* gy, const void* y, void* g, float* db
 }
 
 // ---- discriminator stem entry points
+static int strip_grid(int B, int H, int W) {
+  const long long nstrips = (long long)B * H * ((W + 3) / 4);
+  long long g = (nstrips + 255) / 256;
+  if (g > 148LL * 32) g = 148LL * 32;
+  return (int)g;
+}
 extern "C" int wu_conv3to3_fprop(const float* x, const float* w, const float* bias, float* y, int B,
                                  int H, int W, wu_stream_t stream) {
   WU_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "wu_conv3to3_fprop: bad args");
-  const long long npix = (long long)B * H * W;
-  long long g = (npix + 255) / 256;
-  if (g > 148LL * 16) g = 148LL * 16;
-  conv3to3_fprop_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W);
-  WU_CHECK_LAUNCH("conv3to3_fprop_kernel");
+  conv3to3_strip_kernel<false><<<strip_grid(B, H, W), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B,
+                                                                                    H, W);
+  WU_CHECK_LAUNCH("conv3to3_strip_kernel");
   return WU_OK;
 }
 extern "C" size_t wu_conv3to3_bprop_workspace_bytes(void) {
@@ -284,14 +314,22 @@ extern "C" size_t wu_conv3to3_bprop_workspace_bytes(void) {
 extern "C" int wu_conv3to3_bprop(const float* g_h1, const float* x, const float* w, float* g_x,
                                  float* dw, float* db, int B, int H, int W, void* workspace,
                                  size_t workspace_bytes, wu_stream_t stream) {
-  WU_REQUIRE(g_h1 && x && w && dw && workspace && B > 0 && H > 0 && W > 0,
-             "wu_conv3to3_bprop: bad args");
-  WU_REQUIRE(workspace_bytes >= wu_conv3to3_bprop_workspace_bytes(),
-             "wu_conv3to3_bprop: workspace %zu too small", workspace_bytes);
+  WU_REQUIRE(g_h1 && x && w && B > 0 && H > 0 && W > 0, "wu_conv3to3_bprop: bad args");
+  WU_REQUIRE(g_x || dw, "wu_conv3to3_bprop: nothing to compute");
   cudaStream_t st = (cudaStream_t)stream;
-  conv3to3_bprop_kernel<<<kStemBwdBlocks, 256, 0, st>>>(g_h1, x, w, g_x, (float*)workspace, B, H, W);
-  WU_CHECK_LAUNCH("conv3to3_bprop_kernel");
-  conv3to3_bprop_final_kernel<<<1, 96, 0, st>>>((const float*)workspace, dw, db, kStemBwdBlocks);
-  WU_CHECK_LAUNCH("conv3to3_bprop_final_kernel");
+  if (dw != nullptr) {
+    WU_REQUIRE(workspace && workspace_bytes >= wu_conv3to3_bprop_workspace_bytes(),
+               "wu_conv3to3_bprop: workspace %zu too small", workspace_bytes);
+    int blocks = strip_grid(B, H, W);
+    if (blocks > kStemBwdBlocks) blocks = kStemBwdBlocks;
+    conv3to3_wgrad_kernel<<<blocks, 256, 0, st>>>(g_h1, x, (float*)workspace, B, H, W);
+    WU_CHECK_LAUNCH("conv3to3_wgrad_kernel");
+    conv3to3_bprop_final_kernel<<<1, 96, 0, st>>>((const float*)workspace, dw, db, blocks);
+    WU_CHECK_LAUNCH("conv3to3_bprop_final_kernel");
+  }
+  if (g_x != nullptr) {  // data gradient = the same convolution with transposed, flipped weights
+    conv3to3_strip_kernel<true><<<strip_grid(B, H, W), 256, 0, st>>>(g_h1, w, nullptr, g_x, B, H, W);
+    WU_CHECK_LAUNCH("conv3to3_strip_kernel<flip>");
+  }
   return WU_OK;
 }
