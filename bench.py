@@ -336,13 +336,52 @@ def run_ours(args):
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64> @ dconv_up1.0 fprop (192->64, "
+        roof = {"bound": "tensor", "kernel": "conv3x3_igemm_v2_kernel<64, 4> @ dconv_up1.0 fprop (192->64, "
                 f"{S}x{S}, batch {B})", "achieved": dom["fprop_tflops"], "peak": peak_burst,
                 "unit": "TFLOP/s", "frac": dom["fprop_tflops"] / peak_burst, "traffic": traffic,
                 "peak_source": peak_src + ", burst (kernel timed alone)",
                 "all_layers": {k: {"tflops": v[0] / v[1] / 1e9, "frac": v[0] / v[1] / 1e9 / peak_burst}
                                for k, v in tot.items()},
                 "per_layer": per_layer}
+        # ---- the HBM-bound fused ops of the generator, each timed alone at its largest site:
+        # algorithmic bytes (tensors read + written once) / time vs the measured HBM peak
+        def hbm_line(name, nbytes, fn):
+            t = time_ms(fn)
+            return {"kernel": name, "algorithmic_bytes": nbytes, "ms": t, "achieved_gbs": nbytes / t / 1e6,
+                    "frac_of_hbm_peak": nbytes / t / 1e6 / hbm}
+
+        px = B * S * S
+        img_r = resident[0][0]
+        w1 = torch.randn(64, 3, 3, 3, device=dev) * 0.2
+        b1 = torch.zeros(64, device=dev)
+        dy64 = torch.randn(B, S, S, 64, device=dev).to(torch.bfloat16)
+        y64 = torch.randn(B, S, S, 64, device=dev).abs().to(torch.bfloat16)
+        gp64 = torch.randn(B, S // 2, S // 2, 64, device=dev).to(torch.bfloat16)
+        x128 = torch.randn(B, S // 2, S // 2, 128, device=dev).to(torch.bfloat16)
+        gu128 = torch.randn(B, S, S, 128, device=dev).to(torch.bfloat16)
+        lw, lb = torch.randn(512, nc, device=dev) * 0.3, torch.zeros(512, device=dev)
+        cond = resident[0][1]
+        wl, bl = torch.randn(3, 64, 1, 1, device=dev) * 0.1, torch.zeros(3, device=dev)
+        _, st_ad = K.adain_up_drop(x128, cond, lw, lb, 1e-5, 0.3, 7, None)
+        hbm_ops = [
+            hbm_line("conv_k27_fprop (3->64 + ReLU, tcgen05 tf32)", px * (12 + 128),
+                     lambda: K.conv_first(img_r, w1, b1)),
+            hbm_line("conv_k27_wgrad (3->64, tcgen05)", px * (12 + 128),
+                     lambda: K.conv_first_wgrad(img_r, dy64)),
+            hbm_line("adain_stats + style + adain_up_drop_fwd (128 ch, 128^2 -> 256^2, Philox dropout)",
+                     px // 4 * 256 * 2 + px * (256 + 16),
+                     lambda: K.adain_up_drop(x128, cond, lw, lb, 1e-5, 0.3, 7, None)),
+            hbm_line("adain backward: adjoint + style + apply (128 ch)",
+                     px * (256 + 16) + px // 4 * 256 * 5,
+                     lambda: K.adain_up_drop_bwd(gu128, x128, cond, lw, lb, st_ad)),
+            hbm_line("maxpool2_fwd (64 ch, 256^2)", px * 128 + px // 4 * 128, lambda: K.maxpool2(y64)),
+            hbm_line("maxpool2_bwd (64 ch, merges skip + pooled gradients, ReLU mask)",
+                     px * 128 * 3 + px // 4 * 128, lambda: K.maxpool2_bwd(y64, gp64, dy64)),
+            hbm_line("conv_last_tanh_fprop (64->3)", px * (128 + 12),
+                     lambda: K.conv_last_tanh(y64, wl, bl)),
+        ]
+        roof["hbm_bound_ops"] = {"peak_gbs": hbm, "peak_source": peak_src, "ops": hbm_ops}
+        del dy64, y64, gp64, x128, gu128
         # ---- batched transfer inference (inf_1year_signals.py:98-107): one image x 1024 signals,
         # sharded by batch across ranks, no collective; train-mode dropout as the reference runs it
         n_sig = 1024
@@ -399,7 +438,8 @@ def run_ours(args):
                        "parallelism": f"dp{world}",
                        "l2": "inputs and activations (GBs per step) far exceed the 126 MB L2; no flush",
                        "generator": "sm_100a kernels (this repo)",
-                       "discriminator": "PyTorch/cuDNN bf16 autocast (SURVEY §8 f1, next row)"},
+                       "discriminator": "sm_100a kernels (this repo; bf16 activations, fp32 spectral norm), "
+                                        "512-wide projection head on PyTorch"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
