@@ -151,3 +151,34 @@ def test_oracle_train_step_matches_golden_curve():
         # thread-count dependent summation order shows up after an Adam step or two (lr 1e-3)
         tol = 1e-5 if i == 0 else 2e-3
         assert np.allclose(got, z["curve"][i], rtol=tol, atol=tol), (i, got, z["curve"][i])
+
+
+def test_checkpoint_roundtrip_with_reference_format(tmp_path):
+    """the trainers' checkpoint dict ({'inference', 'discriminator', 'epoch',
+    'global_step'}, t_cls_train.py:399-406) written here loads strictly into fresh modules, and a
+    file written the way the reference writes it (plain torch.save of that dict) loads here."""
+    import torch
+    from weather_unet_b200 import Conditional_UNet
+    from weather_unet_b200.disc import SNDisc
+    from weather_unet_b200 import checkpoint as ck
+    torch.manual_seed(5)
+    g, d = Conditional_UNet(5), SNDisc(5)
+    path = ck.checkpoint_name(str(tmp_path), "cUNet_c_test", 3, 1234)
+    assert path.endswith("cUNet_c_test/cUNet_c_test_e0003_s1234.pt")
+    assert ck.save_checkpoint(path, g, d, 3, 1234) == path
+    assert ck.latest_checkpoint(str(tmp_path), "cUNet_c_test") == path
+    torch.manual_seed(6)
+    g2, d2 = Conditional_UNet(5), SNDisc(5)
+    assert ck.load_checkpoint(path, g2, d2) == (3, 1234)
+    for a, b in zip(list(g.state_dict().values()) + list(d.state_dict().values()),
+                    list(g2.state_dict().values()) + list(d2.state_dict().values())):
+        assert torch.equal(a, b)
+    # a reference-written file: torch.save of the same dict, state_dicts straight from the modules
+    ref_path = str(tmp_path / "ref_style.pt")
+    torch.save({"inference": g.state_dict(), "discriminator": d.state_dict(), "epoch": 7,
+                "global_step": 99}, ref_path)
+    assert ck.load_checkpoint(ref_path, Conditional_UNet(5), SNDisc(5)) == (7, 99)
+    # inference scripts only read sd['inference'] (demo.py:52-53)
+    assert ck.load_checkpoint(ref_path, Conditional_UNet(5)) == (7, 99)
+    with pytest.raises(RuntimeError):
+        ck.load_checkpoint(ref_path, Conditional_UNet(6))  # strict, like the reference
