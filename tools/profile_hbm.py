@@ -21,7 +21,26 @@ y256 = torch.randn(B, 256, 256, 64, device=dev).to(bf)
 gp = torch.randn(B, 128, 128, 64, device=dev).to(bf)
 
 
+# discriminator pieces (disc.py:28-31 at batch 64): stem + first trunk block, forward and backward
+w0s = (torch.randn(3, 3, 3, 3, device=dev) * 0.3).requires_grad_(True)
+b0s = torch.zeros(3, device=dev, requires_grad=True)
+w1s = (torch.randn(64, 3, 3, 3, device=dev) * 0.2).requires_grad_(True)
+b1s = torch.zeros(64, device=dev, requires_grad=True)
+wa = (torch.randn(64, 64, 3, 3, device=dev) * 0.04).requires_grad_(True)
+ba = torch.zeros(64, device=dev, requires_grad=True)
+wb = (torch.randn(128, 64, 3, 3, device=dev) * 0.04).requires_grad_(True)
+bb = torch.zeros(128, device=dev, requires_grad=True)
+img_g = img.clone().requires_grad_(True)
+
+
+def disc_part():
+    c1 = K.disc_stem(img_g, w0s, b0s, w1s, b1s, 0.2)
+    c2 = K.disc_block(c1, wa, ba, wb, bb, 0.2)
+    c2.float().sum().backward()
+
+
 def run():
+    disc_part()
     K.conv_first(img, w1, b1)
     K.conv_first_wgrad(img, dy256)
     u, st = K.adain_up_drop(x128, cond, lw, lb, 1e-5, 0.3, 1234, None)

@@ -851,7 +851,8 @@ struct WgradParams2 {
   int tiles_w, tiles_h, batch;
   int pix_tiles;
   int cout, cin_total;
-  float* partial;  // [splits][9*cin_total][cout]
+  float* partial;       // [splits][9*cin_total][cout]
+  float* bias_partial;  // [4*splits][cout] column sums of dY (bias gradient), or null
 };
 
 template <int BN, int NC>
@@ -912,10 +913,15 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
     tma_prefetch_desc(&tmX1);
     tma_prefetch_desc(&tmY);
   }
+  // Bias gradient db[co] = sum_px dY[px][co]: the dY tiles pass through this CTA's shared memory
+  // anyway, so the four warps that otherwise only drain the accumulator at the end add them up
+  // column-wise while the MMAs run (copy group 0 of every (split, n tile) only: all groups of a split
+  // see the same tiles).  A separate pass re-read every dY from HBM (0.86 ms per training iteration).
+  const bool do_bias = p.bias_partial != nullptr && grp == 0;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(full_bar(i), 1);
-      mbar_init(empty_bar(i), 1);
+      mbar_init(empty_bar(i), do_bias ? 5 : 1);  // MMA commit (+ one arrival per summing warp)
     }
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
@@ -1031,6 +1037,41 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int half = row >> 6, r64 = row & 63;
+    if (do_bias) {
+      // warp q sums pixel rows 16q .. 16q+15 of every dY tile; lane = a pair of adjacent channels
+      // (4 bytes) of each 64-channel atom.  The tile is 128B-swizzled: 16-byte chunk c of row r
+      // sits at chunk position c ^ (r & 7); a warp reads one 128-byte row per load (no conflicts).
+      float acc[BN / 64][2];
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j) acc[j][0] = acc[j][1] = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(full_bar(stage), phase);
+        const uint8_t* bt = smem + stage * Cfg::kStageBytes + Cfg::kABytes;
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) {
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = q * 16 + rr;
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(
+                bt + j * Cfg::kAtomBytes + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+            acc[j][0] += bf16lo(v);
+            acc[j][1] += bf16hi(v);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      float* bp = p.bias_partial + ((size_t)(z * 4 + q)) * p.cout + n0;
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j)
+        *reinterpret_cast<float2*>(bp + j * 64 + lane * 2) = make_float2(acc[j][0], acc[j][1]);
+    }
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const int nblocks = nc + ((nc + 1) >> 1);
@@ -1440,6 +1481,8 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     q.cout = cout;
     q.cin_total = cin;
     q.partial = reinterpret_cast<float*>(workspace);
+    float* bscratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.partial_bytes);
+    q.bias_partial = db != nullptr ? bscratch : nullptr;  // 4 * splits <= kBiasGradBlocks rows
     CUtensorMap x0, x1, ym;
     int rc;
     if ((rc = make_act_tmap(&x0, src0, B, H, W, c0, c0, 8, 10)) != WU_OK) return rc;
@@ -1455,7 +1498,13 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     else if (pl.bn == 64) rc = launch_wgrad2<64, 5>(x0, x1, ym, q, grid, st);
     else rc = launch_wgrad2<128, 2>(x0, x1, ym, q, grid, st);
     if (rc != WU_OK) return rc;
-    return wgrad_finish(q.partial, dw, db, dy, workspace, pl, cin, cout, B, H, W, st);
+    if ((rc = wgrad_fold(q.partial, pl.splits, cin, cout, dw, dy, 0, nullptr, nullptr, st)) != WU_OK)
+      return rc;
+    if (db != nullptr) {  // fold the in-kernel column sums: [4 * splits][cout] -> db
+      bias_grad_final_kernel<<<(cout + 31) / 32, 256, 0, st>>>(bscratch, db, 4 * pl.splits, cout);
+      WU_CHECK_LAUNCH("bias_grad_final_kernel");
+    }
+    return WU_OK;
   }
   WgradParams p;
   p.c0_blocks = c0 / 64;
