@@ -247,19 +247,51 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total / 1e3)
     last = {k: float(v) for k, v in losses.items()}
 
-    # ---- end to end: pinned host batch -> device every step, losses read back every step
-    stage = [torch.empty_like(t, device=dev) for t in host[0]]
-    d2h_bytes = 0
+    # ---- end to end: pinned host batch -> device every step, losses read back every step.
+    # The loop is what a training script with a pinned-memory loader does: the NEXT batch is copied
+    # host -> device on a copy stream while the current iteration computes (two device staging slots),
+    # and the losses of iteration i are read on the host (pinned buffer, event) while iteration i+1
+    # runs; every copy and every read happens inside the timed region, once per step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [[torch.empty_like(t, device=dev) for t in host[0]] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_bytes = loss_host[0].numel() * loss_host[0].element_size()
+    main_stream = torch.cuda.current_stream()
+
+    def upload(i):
+        k = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])  # the iteration that used this slot has finished
+            for dst, src in zip(slots[k], host[i % n_host]):
+                dst.copy_(src, non_blocking=True)
+            ready[k].record(copy_stream)
+
+    for ev in consumed:
+        ev.record(main_stream)
     barrier()
+    read_back = []
     e0.record()
+    upload(0)
     for i in range(args.steps):
-        for dst, src in zip(stage, host[i % n_host]):
-            dst.copy_(src, non_blocking=True)
-        losses = trainer.step(*stage)
-        got = torch.stack([losses["d_loss"], losses["g_loss"]]).cpu()  # D2H read of the step result
-        d2h_bytes = got.numel() * got.element_size()
+        k = i % 2
+        if i + 1 < args.steps:
+            upload(i + 1)
+        main_stream.wait_event(ready[k])
+        losses = trainer.step(*slots[k])
+        consumed[k].record(main_stream)
+        loss_host[k].copy_(torch.stack([losses["d_loss"], losses["g_loss"]]), non_blocking=True)
+        loss_done[k].record(main_stream)
+        if i >= 1:  # host reads the previous iteration's losses while this one runs
+            loss_done[1 - k].synchronize()
+            read_back.append(loss_host[1 - k].tolist())
+    loss_done[(args.steps - 1) % 2].synchronize()
+    read_back.append(loss_host[(args.steps - 1) % 2].tolist())
     e1.record()
     barrier()
+    assert len(read_back) == args.steps
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
