@@ -718,7 +718,8 @@ __device__ __forceinline__ float bilinear_adjoint_w(int D, int s, float ratio, i
 // written, added to the sums, and the accumulators shift.  i0(Y) is the same for the whole block.
 // keep comes from the byte tensor the forward pass stored (keep_bits == nullptr: no dropout).
 constexpr int kAdjRows = 16;
-__global__ void __launch_bounds__(256)
+// (three blocks per SM: 80 registers; at the natural 112 the kernel was latency bound at 25 % occupancy)
+__global__ void __launch_bounds__(256, 3)
 adain_up_drop_adjoint_kernel(const __nv_bfloat16* __restrict__ gu, const uint8_t* __restrict__ keep_bits,
                              const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                              const float* __restrict__ rstd, __nv_bfloat16* __restrict__ gz,

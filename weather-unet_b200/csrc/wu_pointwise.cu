@@ -171,8 +171,8 @@ conv3to3_strip_kernel(const float* __restrict__ x, const float* __restrict__ w,
 // Weight / bias gradient of Conv2d(3,3,3,padding=1): per-block partial sums of
 // dw0[co][ci][r][s] = sum g_h1[co] * x[ci][shifted], db0[co] = sum g_h1[co]; same 4-pixel strips,
 // 84 accumulators per thread.
-constexpr int kStemBwdBlocks = 148 * 2;
-__global__ void __launch_bounds__(256)
+constexpr int kStemBwdBlocks = 148 * 4;
+__global__ void __launch_bounds__(256, 2)
 conv3to3_wgrad_kernel(const float* __restrict__ gh, const float* __restrict__ x,
                       float* __restrict__ partial, int B, int H, int W) {
   __shared__ float red[8][84];
