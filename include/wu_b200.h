@@ -63,6 +63,14 @@ int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1, int c1, i
                            const void* relu_mask_src, void* dst, int cout, int B, int H, int W,
                            wu_stream_t stream);
 
+/* The generator's last two layers in one kernel (cunet.py:78-82): dst = relu(conv3x3(src) + bias)
+ * with 64 output channels (dconv_up1.2, kept for the backward pass) and, from the same registers,
+ *   y[b,o,h,w] = tanh(last_b[o] + sum_c last_w[o][c] * dst[b,h,w,c])       (conv_last + Tanh)
+ * last_w fp32 [3][64], last_b fp32 [3] (may be NULL), y fp32 NCHW [B][3][H][W]. */
+int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_packed, const float* bias, void* dst,
+                          const float* last_w, const float* last_b, float* y, int B, int H, int W,
+                          wu_stream_t stream);
+
 /* Weight + bias gradient of the same convolution (autograd of nets.py:20,22):
  *   dw[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * src[b,h+r-1,w+s-1,ci]     (fp32, overwritten)
  *   db[co]           = sum_{b,h,w} dy[b,h,w,co]                              (fp32, may be NULL)

@@ -88,8 +88,10 @@ class _CUNetFn(torch.autograd.Function):
         up2a, up2b = block(u2, conv2, "dconv_up2")
         u1, st1 = K.adain_up_drop(up2b, c, P["adain1.l1.weight"], P["adain1.l1.bias"], eps[2], p_drop,
                                   seed + 2, masks[2])
-        up1a, up1b = block(u1, conv1, "dconv_up1")
-        y = K.conv_last_tanh(up1b, P["conv_last.weight"], P["conv_last.bias"])
+        # last block: its second convolution also applies conv_last + tanh from registers (cunet.py:78-82)
+        up1a = K.conv3x3(u1, conv1, wf("dconv_up1.0.weight"), P["dconv_up1.0.bias"], True, None, 64)
+        up1b, y = K.conv3x3_last(up1a, wf("dconv_up1.2.weight"), P["dconv_up1.2.bias"],
+                                 P["conv_last.weight"], P["conv_last.bias"])
 
         ctx.acts = dict(x=x, c=c, a1=a1, conv1=conv1, p1=p1, d2a=d2a, conv2=conv2, p2=p2, d3a=d3a,
                         conv3=conv3, p3=p3, d4a=d4a, x4=x4, u3=u3, up3a=up3a, up3b=up3b, u2=u2,
@@ -218,8 +220,10 @@ def transfer_forward(module, x1, c, masks, seed):
     h = block(u2, conv2, "dconv_up2", bcast=True)
     u1, _ = K.adain_up_drop(h, c, P["adain1.l1.weight"], P["adain1.l1.bias"], module.adain1.eps,
                             p_drop, seed + 2, masks[2])
-    h = block(u1, conv1, "dconv_up1", bcast=True)
-    return K.conv_last_tanh(h, P["conv_last.weight"], P["conv_last.bias"])
+    a = K.conv3x3(u1, conv1, wf("dconv_up1.0.weight"), P["dconv_up1.0.bias"], True, None, 64,
+                  src1_bcast=True)
+    return K.conv3x3_last(a, wf("dconv_up1.2.weight"), P["dconv_up1.2.bias"], P["conv_last.weight"],
+                          P["conv_last.bias"])[1]
 
 
 def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=None):

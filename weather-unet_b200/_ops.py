@@ -36,6 +36,17 @@ def conv3x3(src0, src1, w_packed, bias, relu, mask, cout, src1_bcast=False):
     return dst
 
 
+def conv3x3_last(src, w_packed, bias, last_w, last_b):
+    """dconv_up1.2 + conv_last + tanh in one kernel (wu_conv3x3_fprop_last):
+    -> (relu(conv3x3(src)) NHWC bf16 (B,H,W,64), tanh(conv1x1) fp32 NCHW (B,3,H,W))."""
+    B, H, W, cin = src.shape
+    dst = _act(B, H, W, 64, src)
+    y = torch.empty((B, 3, H, W), dtype=torch.float32, device=src.device)
+    call("wu_conv3x3_fprop_last", ptr(src), cin, ptr(w_packed), ptr(bias), ptr(dst), ptr(last_w),
+         ptr(last_b), ptr(y), B, H, W, stream())
+    return dst, y
+
+
 def conv3x3_wgrad(src0, src1, dy, want_bias=True):
     """-> (dw fp32 [cout][cin][3][3], db fp32 [cout] or None)."""
     B, H, W, c0 = src0.shape

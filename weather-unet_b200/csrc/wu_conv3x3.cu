@@ -354,6 +354,11 @@ struct ConvParams2 {
   int b1_mul;  // 1, or 0 when source 1 has batch 1 and is shared by every image
   const float* bias;
   const __nv_bfloat16* mask;
+  // LAST instantiation (dconv_up1.2): Conv2d(64, 3, 1) + Tanh (cunet.py:39-40,80-82) on the tile while
+  // it is still in registers: last_w fp32 [3][64], last_b [3], last_y fp32 NCHW [B][3][H][W]
+  const float* last_w;
+  const float* last_b;
+  float* last_y;
 };
 
 template <int BN, int T>
@@ -372,7 +377,7 @@ struct ConvCfg2 {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int T>
+template <int BN, int T, bool LAST>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
                         const __grid_constant__ CUtensorMap tmA1,
@@ -423,6 +428,11 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
       mbar_init(tempty_bar(i), 128);
     }
     fence_mbar_init();
+  }
+  if (LAST) {  // the 1x1 weights live in the ReLU-mask staging area (unused in a forward pass)
+    float* lw = reinterpret_cast<float*>(smem + (mask_base - base));
+    for (int i = threadIdx.x; i < 3 * 64 + 3; i += blockDim.x)
+      lw[i] = i < 192 ? p.last_w[i] : (p.last_b != nullptr ? p.last_b[i - 192] : 0.f);
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
@@ -588,6 +598,39 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
           uint32_t pk0[16], pk1[16];
           epilogue_half_r(v0, bptr, p.relu, has_mask, mk, pk0);
           epilogue_half_r(v1, bptr ? bptr + 32 : nullptr, p.relu, has_mask, mk + 4, pk1);
+          if (LAST) {
+            // y[b, o, h, w] = tanh(last_b[o] + sum_c last_w[o][c] * relu(conv)[c]): this thread holds
+            // all 64 channels of its pixel (BN == 64), fp32, after bias + ReLU
+            const float4* lw4 = reinterpret_cast<const float4*>(smem + (mask_base - base));
+            const float* lb = reinterpret_cast<const float*>(smem + (mask_base - base)) + 192;
+            float a0 = lb[0], a1 = lb[1], a2 = lb[2];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w0v = lw4[j], w1v = lw4[16 + j], w2v = lw4[32 + j];
+              const float x0 = __uint_as_float(v0[4 * j]), x1 = __uint_as_float(v0[4 * j + 1]);
+              const float x2 = __uint_as_float(v0[4 * j + 2]), x3 = __uint_as_float(v0[4 * j + 3]);
+              a0 = fmaf(x0, w0v.x, a0); a0 = fmaf(x1, w0v.y, a0); a0 = fmaf(x2, w0v.z, a0); a0 = fmaf(x3, w0v.w, a0);
+              a1 = fmaf(x0, w1v.x, a1); a1 = fmaf(x1, w1v.y, a1); a1 = fmaf(x2, w1v.z, a1); a1 = fmaf(x3, w1v.w, a1);
+              a2 = fmaf(x0, w2v.x, a2); a2 = fmaf(x1, w2v.y, a2); a2 = fmaf(x2, w2v.z, a2); a2 = fmaf(x3, w2v.w, a2);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w0v = lw4[8 + j], w1v = lw4[24 + j], w2v = lw4[40 + j];
+              const float x0 = __uint_as_float(v1[4 * j]), x1 = __uint_as_float(v1[4 * j + 1]);
+              const float x2 = __uint_as_float(v1[4 * j + 2]), x3 = __uint_as_float(v1[4 * j + 3]);
+              a0 = fmaf(x0, w0v.x, a0); a0 = fmaf(x1, w0v.y, a0); a0 = fmaf(x2, w0v.z, a0); a0 = fmaf(x3, w0v.w, a0);
+              a1 = fmaf(x0, w1v.x, a1); a1 = fmaf(x1, w1v.y, a1); a1 = fmaf(x2, w1v.z, a1); a1 = fmaf(x3, w1v.w, a1);
+              a2 = fmaf(x0, w2v.x, a2); a2 = fmaf(x1, w2v.y, a2); a2 = fmaf(x2, w2v.z, a2); a2 = fmaf(x3, w2v.w, a2);
+            }
+            const int hh = h0 + 16 * t + ph, ww = w0 + pw;
+            if (hh < p.H && ww < p.W) {
+              const size_t hw = (size_t)p.H * p.W;
+              float* yo = p.last_y + (size_t)b * 3 * hw + (size_t)hh * p.W + ww;
+              yo[0] = tanhf(a0);
+              yo[hw] = tanhf(a1);
+              yo[2 * hw] = tanhf(a2);
+            }
+          }
           const uint32_t sbuf = staging_base + (store_count & 1u) * 16384u;
           ++store_count;
           if (issuer) tma_store_wait_read<1>();
@@ -617,18 +660,18 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN, int T>
+template <int BN, int T, bool LAST = false>
 static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
                         const CUtensorMap& dm, const ConvParams2& p, cudaStream_t st) {
   using Cfg = ConvCfg2<BN, T>;
   static bool attr_done = false;
   if (!attr_done) {
-    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T>,
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv3x3_igemm_v2_kernel<BN, T><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
+  conv3x3_igemm_v2_kernel<BN, T, LAST><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_v2_kernel");
   return WU_OK;
 }
@@ -1356,6 +1399,8 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     q.b1_mul = src1_bcast ? 0 : 1;
     q.bias = bias;
     q.mask = (const __nv_bfloat16*)relu_mask_src;
+    q.last_w = q.last_b = nullptr;
+    q.last_y = nullptr;
     CUtensorMap a0, a1, bm, dm;
     int rc;
     if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, 8, 16 * T + 2)) != WU_OK) return rc;
@@ -1410,6 +1455,40 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     case 128: return launch_conv<128>(a0, a1, bm, dm, p, st);
     default: return launch_conv<256>(a0, a1, bm, dm, p, st);
   }
+}
+
+extern "C" int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_packed, const float* bias,
+                                     void* dst, const float* last_w, const float* last_b, float* y,
+                                     int B, int H, int W, wu_stream_t stream) {
+  WU_REQUIRE(src && w_packed && dst && last_w && y, "wu_conv3x3_fprop_last: null pointer");
+  WU_REQUIRE(B > 0 && H > 0 && W > 0, "wu_conv3x3_fprop_last: bad shape B=%d H=%d W=%d", B, H, W);
+  WU_REQUIRE(cin > 0 && cin % 64 == 0, "wu_conv3x3_fprop_last: cin=%d must be a positive multiple of 64", cin);
+  constexpr int T = 4;
+  ConvParams2 q;
+  q.c0_blocks = q.ctot_blocks = cin / 64;
+  q.tiles_w = (W + 7) / 8;
+  q.tiles_h = (H + 16 * T - 1) / (16 * T);
+  q.batch = B;
+  q.n_tiles = 1;
+  const long long nt = (long long)B * q.tiles_w * q.tiles_h;
+  WU_REQUIRE(nt < (1LL << 31), "wu_conv3x3_fprop_last: too many tiles");
+  q.num_tiles = (int)nt;
+  q.H = H;
+  q.W = W;
+  q.cout = 64;
+  q.relu = 1;
+  q.b1_mul = 1;
+  q.bias = bias;
+  q.mask = nullptr;
+  q.last_w = last_w;
+  q.last_b = last_b;
+  q.last_y = y;
+  CUtensorMap a0, bm, dm;
+  int rc;
+  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
+  if ((rc = make_mat_tmap(&bm, w_packed, 64, 9 * cin, 64)) != WU_OK) return rc;
+  if ((rc = make_act_tmap(&dm, dst, B, H, W, 64, 64, 8, 16)) != WU_OK) return rc;
+  return launch_conv2<64, T, true>(a0, a0, bm, dm, q, (cudaStream_t)stream);
 }
 
 // split-K fold into the reference layout + bias gradient (shared with wu_conv_s2.cu)
