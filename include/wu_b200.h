@@ -71,6 +71,12 @@ int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_packed, const 
                           const float* last_w, const float* last_b, float* y, int B, int H, int W,
                           wu_stream_t stream);
 
+/* Convolution + ReLU + nn.MaxPool2d(2) in one kernel (cunet.py:45-46, 48-49): dst as wu_conv3x3_fprop
+ * with relu = 1 (kept: it is the skip tensor), pool_dst NHWC bf16 [B][H/2][W/2][cout] = 2x2 max of dst,
+ * taken from the staged tile in shared memory.  cout = 64 or 128; H, W even. */
+int wu_conv3x3_fprop_pool(const void* src, int cin, const void* w_packed, const float* bias, void* dst,
+                          void* pool_dst, int cout, int B, int H, int W, wu_stream_t stream);
+
 /* Weight + bias gradient of the same convolution (autograd of nets.py:20,22):
  *   dw[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * src[b,h+r-1,w+s-1,ci]     (fp32, overwritten)
  *   db[co]           = sum_{b,h,w} dy[b,h,w,co]                              (fp32, may be NULL)

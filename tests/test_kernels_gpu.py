@@ -189,6 +189,48 @@ def test_conv_first(cuda, B, H, W):
     assert rel(db, dy.sum(dim=(0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 32, 32, 64, 64), (1, 24, 40, 64, 128), (3, 72, 16, 128, 128),
+                                            (1, 256, 256, 64, 64)])
+def test_conv3x3_pool_fused(cuda, B, H, W, cin, cout):
+    """conv3x3 + ReLU + MaxPool2d(2) in one kernel (cunet.py:45-46): both outputs bit-identical to the
+    separate convolution and pooling kernels."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(B + H + cin + cout)
+    x = nhwc(bf(torch.randn(B, cin, H, W, generator=g)).to(cuda))
+    w = bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(cuda)
+    b = (torch.randn(cout, generator=g) * 0.1).to(cuda)
+    wf, _ = K.pack_conv3x3_weights(w, need_dgrad=False)
+    full, pooled = K.conv3x3_pool(x, wf, b, cout)
+    ref_full = K.conv3x3(x, None, wf, b, True, None, cout)
+    assert torch.equal(full, ref_full)
+    assert torch.equal(pooled, K.maxpool2(ref_full))
+    assert torch.equal(nchw(pooled), F.max_pool2d(nchw(ref_full), 2))
+
+
+@pytest.mark.parametrize("B,H,W,cin", [(2, 32, 32, 64), (1, 24, 40, 64), (1, 72, 16, 128)])
+def test_conv3x3_last_fused(cuda, B, H, W, cin):
+    """dconv_up1.2 + conv_last + tanh in one kernel (cunet.py:78-82) against PyTorch fp32, and
+    against the two separate kernels."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator(device="cpu").manual_seed(B + H + cin)
+    x = bf(torch.randn(B, cin, H, W, generator=g)).to(cuda)
+    w = bf(torch.randn(64, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(cuda)
+    b = (torch.randn(64, generator=g) * 0.1).to(cuda)
+    lw = (torch.randn(3, 64, 1, 1, generator=g) * 0.2).to(cuda)
+    lb = (torch.randn(3, generator=g) * 0.1).to(cuda)
+    wf, _ = K.pack_conv3x3_weights(w, need_dgrad=False)
+    h, y = K.conv3x3_last(nhwc(x), wf, b, lw, lb)
+    h_ref = F.relu(F.conv2d(x, w, b, padding=1))
+    assert rel(nchw(h), h_ref) < 6e-3
+    y_ref = torch.tanh(F.conv2d(h_ref, lw, lb))
+    assert (y - y_ref).abs().max().item() < 5e-3
+    h2 = K.conv3x3(nhwc(x), None, wf, b, True, None, 64)
+    assert torch.equal(h, h2)
+    # the stand-alone kernel reads the bf16-rounded activations (64 terms x 2^-9 relative each)
+    y2 = K.conv_last_tanh(h2, lw, lb)
+    assert (y - y2).abs().max().item() < 3e-2
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 24, 40), (3, 64, 64)])
 def test_conv_last_tanh(cuda, B, H, W):
     from weather_unet_b200 import _ops as K

@@ -72,10 +72,10 @@ class _CUNetFn(torch.autograd.Function):
 
         # encoder (cunet.py:45-54)
         a1 = K.conv_first(x, P["dconv_down1.0.weight"], P["dconv_down1.0.bias"])
-        conv1 = K.conv3x3(a1, None, wf("dconv_down1.2.weight"), P["dconv_down1.2.bias"], True, None, 64)
-        p1 = K.maxpool2(conv1)
-        d2a, conv2 = block(p1, None, "dconv_down2")
-        p2 = K.maxpool2(conv2)
+        # the first two pooling layers come out of the producing convolution's epilogue (cunet.py:46,49)
+        conv1, p1 = K.conv3x3_pool(a1, wf("dconv_down1.2.weight"), P["dconv_down1.2.bias"], 64)
+        d2a = K.conv3x3(p1, None, wf("dconv_down2.0.weight"), P["dconv_down2.0.bias"], True, None, 128)
+        conv2, p2 = K.conv3x3_pool(d2a, wf("dconv_down2.2.weight"), P["dconv_down2.2.bias"], 128)
         d3a, conv3 = block(p2, None, "dconv_down3")
         p3 = K.maxpool2(conv3)
         d4a, x4 = block(p3, None, "dconv_down4")
@@ -208,9 +208,10 @@ def transfer_forward(module, x1, c, masks, seed):
         return K.conv3x3(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], True, None, cout)
 
     a1 = K.conv_first(x1, P["dconv_down1.0.weight"], P["dconv_down1.0.bias"])
-    conv1 = K.conv3x3(a1, None, wf("dconv_down1.2.weight"), P["dconv_down1.2.bias"], True, None, 64)
-    conv2 = block(K.maxpool2(conv1), None, "dconv_down2")
-    conv3 = block(K.maxpool2(conv2), None, "dconv_down3")
+    conv1, p1 = K.conv3x3_pool(a1, wf("dconv_down1.2.weight"), P["dconv_down1.2.bias"], 64)
+    d2a = K.conv3x3(p1, None, wf("dconv_down2.0.weight"), P["dconv_down2.0.bias"], True, None, 128)
+    conv2, p2 = K.conv3x3_pool(d2a, wf("dconv_down2.2.weight"), P["dconv_down2.2.bias"], 128)
+    conv3 = block(p2, None, "dconv_down3")
     x4 = block(K.maxpool2(conv3), None, "dconv_down4")
     u3, _ = K.adain_up_drop(x4, c, P["adain3.l1.weight"], P["adain3.l1.bias"], module.adain3.eps,
                             p_drop, seed, masks[0], x_bcast=True)

@@ -25,6 +25,7 @@ SIGNATURES = {
     "wu_conv3x3_fprop": (I, [P, I, P, I, P, P, I, P, P, I, I, I, I, P]),
     "wu_conv3x3_fprop_bcast": (I, [P, I, P, I, I, P, P, I, P, P, I, I, I, I, P]),
     "wu_conv3x3_fprop_last": (I, [P, I, P, P, P, P, P, P, I, I, I, P]),
+    "wu_conv3x3_fprop_pool": (I, [P, I, P, P, P, P, I, I, I, I, P]),
     "wu_conv3x3_wgrad_workspace_bytes": (SZ, [I, I, I, I, I]),
     "wu_conv3x3_wgrad": (I, [P, I, P, I, P, I, I, I, I, P, P, P, SZ, P]),
     "wu_conv_first_fprop": (I, [P, P, P, P, I, I, I, P]),

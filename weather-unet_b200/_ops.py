@@ -47,6 +47,17 @@ def conv3x3_last(src, w_packed, bias, last_w, last_b):
     return dst, y
 
 
+def conv3x3_pool(src, w_packed, bias, cout):
+    """conv3x3 + ReLU + MaxPool2d(2) in one kernel (wu_conv3x3_fprop_pool):
+    -> (full-resolution output (B,H,W,cout), pooled (B,H/2,W/2,cout))."""
+    B, H, W, cin = src.shape
+    dst = _act(B, H, W, cout, src)
+    pooled = _act(B, H // 2, W // 2, cout, src)
+    call("wu_conv3x3_fprop_pool", ptr(src), cin, ptr(w_packed), ptr(bias), ptr(dst), ptr(pooled), cout,
+         B, H, W, stream())
+    return dst, pooled
+
+
 def conv3x3_wgrad(src0, src1, dy, want_bias=True):
     """-> (dw fp32 [cout][cin][3][3], db fp32 [cout] or None)."""
     B, H, W, c0 = src0.shape

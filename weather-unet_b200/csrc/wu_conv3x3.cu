@@ -359,6 +359,9 @@ struct ConvParams2 {
   const float* last_w;
   const float* last_b;
   float* last_y;
+  // POOL instantiation (dconv_down1.2 / dconv_down2.2): nn.MaxPool2d(2) (cunet.py:46,49) of the tile,
+  // taken from the staged bf16 tile before it leaves shared memory: pool_dst NHWC [B][H/2][W/2][cout]
+  __nv_bfloat16* pool_dst;
 };
 
 template <int BN, int T>
@@ -377,7 +380,7 @@ struct ConvCfg2 {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int T, bool LAST>
+template <int BN, int T, bool LAST, bool POOL>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
                         const __grid_constant__ CUtensorMap tmA1,
@@ -649,6 +652,34 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
             if (h0 + 16 * t < p.H) tma_store_4d(&tmD, sbuf, cbase, w0, h0 + 16 * t, b);
             tma_store_commit();
           }
+          if (POOL) {
+            // 2x2 max over the staged [16 x 8 px][64 ch] tile -> 8 x 4 pooled pixels; a task is one
+            // 16-byte chunk of one pooled pixel (256 tasks, two per thread).  Values are post-ReLU
+            // (non-negative bf16), so the unsigned 16-bit SIMD max is the float max.  The staging
+            // buffer is only rewritten after the next chunk's barrier, which every thread reaches
+            // after these reads.
+            const uint8_t* stile = smem + (sbuf - base);
+            const int Hp = p.H >> 1, Wp = p.W >> 1;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int task = et + 128 * half;
+              const int pp = task >> 3, c = task & 7;
+              const int pr = pp >> 2, pc = pp & 3;
+              const int r00 = (2 * pr) * 8 + 2 * pc;
+              uint4 m = *reinterpret_cast<const uint4*>(stile + r00 * 128 + ((c ^ (r00 & 7)) << 4));
+#pragma unroll
+              for (int k = 1; k < 4; ++k) {
+                const int r = r00 + (k & 1) + (k >> 1) * 8;
+                const uint4 q = *reinterpret_cast<const uint4*>(stile + r * 128 + ((c ^ (r & 7)) << 4));
+                m.x = __vmaxu2(m.x, q.x); m.y = __vmaxu2(m.y, q.y);
+                m.z = __vmaxu2(m.z, q.z); m.w = __vmaxu2(m.w, q.w);
+              }
+              const int hp = ((h0 + 16 * t) >> 1) + pr, wp = (w0 >> 1) + pc;
+              if (hp < Hp && wp < Wp)
+                *reinterpret_cast<uint4*>(p.pool_dst + (((size_t)b * Hp + hp) * Wp + wp) * p.cout + cbase +
+                                          c * 8) = m;
+            }
+          }
         }
       }
     }
@@ -660,18 +691,18 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN, int T, bool LAST = false>
+template <int BN, int T, bool LAST = false, bool POOL = false>
 static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
                         const CUtensorMap& dm, const ConvParams2& p, cudaStream_t st) {
   using Cfg = ConvCfg2<BN, T>;
   static bool attr_done = false;
   if (!attr_done) {
-    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST>,
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST, POOL>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv3x3_igemm_v2_kernel<BN, T, LAST><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
+  conv3x3_igemm_v2_kernel<BN, T, LAST, POOL><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_v2_kernel");
   return WU_OK;
 }
@@ -1401,6 +1432,7 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     q.mask = (const __nv_bfloat16*)relu_mask_src;
     q.last_w = q.last_b = nullptr;
     q.last_y = nullptr;
+    q.pool_dst = nullptr;
     CUtensorMap a0, a1, bm, dm;
     int rc;
     if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, 8, 16 * T + 2)) != WU_OK) return rc;
@@ -1483,12 +1515,51 @@ extern "C" int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_pac
   q.last_w = last_w;
   q.last_b = last_b;
   q.last_y = y;
+  q.pool_dst = nullptr;
   CUtensorMap a0, bm, dm;
   int rc;
   if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
   if ((rc = make_mat_tmap(&bm, w_packed, 64, 9 * cin, 64)) != WU_OK) return rc;
   if ((rc = make_act_tmap(&dm, dst, B, H, W, 64, 64, 8, 16)) != WU_OK) return rc;
   return launch_conv2<64, T, true>(a0, a0, bm, dm, q, (cudaStream_t)stream);
+}
+
+extern "C" int wu_conv3x3_fprop_pool(const void* src, int cin, const void* w_packed, const float* bias,
+                                     void* dst, void* pool_dst, int cout, int B, int H, int W,
+                                     wu_stream_t stream) {
+  WU_REQUIRE(src && w_packed && dst && pool_dst, "wu_conv3x3_fprop_pool: null pointer");
+  WU_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
+             "wu_conv3x3_fprop_pool: bad shape B=%d H=%d W=%d (H, W must be even)", B, H, W);
+  WU_REQUIRE(cin > 0 && cin % 64 == 0, "wu_conv3x3_fprop_pool: cin=%d must be a positive multiple of 64", cin);
+  WU_REQUIRE(cout == 64 || cout == 128, "wu_conv3x3_fprop_pool: cout=%d must be 64 or 128", cout);
+  const int T = cout == 64 ? 4 : 2;
+  ConvParams2 q;
+  q.c0_blocks = q.ctot_blocks = cin / 64;
+  q.tiles_w = (W + 7) / 8;
+  q.tiles_h = (H + 16 * T - 1) / (16 * T);
+  q.batch = B;
+  q.n_tiles = 1;
+  const long long nt = (long long)B * q.tiles_w * q.tiles_h;
+  WU_REQUIRE(nt < (1LL << 31), "wu_conv3x3_fprop_pool: too many tiles");
+  q.num_tiles = (int)nt;
+  q.H = H;
+  q.W = W;
+  q.cout = cout;
+  q.relu = 1;
+  q.b1_mul = 1;
+  q.bias = bias;
+  q.mask = nullptr;
+  q.last_w = q.last_b = nullptr;
+  q.last_y = nullptr;
+  q.pool_dst = (__nv_bfloat16*)pool_dst;
+  CUtensorMap a0, bm, dm;
+  int rc;
+  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
+  if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * cin, cout)) != WU_OK) return rc;
+  if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, 8, 16)) != WU_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return cout == 64 ? launch_conv2<64, 4, false, true>(a0, a0, bm, dm, q, st)
+                    : launch_conv2<128, 2, false, true>(a0, a0, bm, dm, q, st);
 }
 
 // split-K fold into the reference layout + bias gradient (shared with wu_conv_s2.cu)
