@@ -50,20 +50,36 @@ bias_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* _
   const int gi = threadIdx.x / lanes, l = threadIdx.x % lanes;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool masked = slope != 1.f;
-  for (long long px = (long long)blockIdx.x * groups + gi; px < npix;
-       px += (long long)gridDim.x * groups) {
-    const long long off = px * C + l * 8;
+  const long long stride = (long long)gridDim.x * groups;
+  auto one = [&](const uint4& gq, const uint4& yq, long long off) {
     float f[8];
-    unpack8p(__ldg(reinterpret_cast<const uint4*>(gy + off)), f);
+    unpack8p(gq, f);
     if (masked) {
       float yv[8];
-      unpack8p(__ldg(reinterpret_cast<const uint4*>(y + off)), yv);
+      unpack8p(yq, yv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = yv[j] > 0.f ? f[j] : f[j] * slope;
     }
     if (masked || g != gy) *reinterpret_cast<uint4*>(g + off) = pack8p(f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  };
+  long long px = (long long)blockIdx.x * groups + gi;
+  for (; px + 3 * stride < npix; px += 4 * stride) {  // eight independent 16-byte loads in flight
+    uint4 gq[4], yq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long off = (px + u * stride) * C + l * 8;
+      gq[u] = __ldg(reinterpret_cast<const uint4*>(gy + off));
+      yq[u] = masked ? __ldg(reinterpret_cast<const uint4*>(y + off)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(gq[u], yq[u], (px + u * stride) * C + l * 8);
+  }
+  for (; px < npix; px += stride) {
+    const long long off = px * C + l * 8;
+    one(__ldg(reinterpret_cast<const uint4*>(gy + off)),
+        masked ? __ldg(reinterpret_cast<const uint4*>(y + off)) : make_uint4(0, 0, 0, 0), off);
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[gi * C + l * 8 + e] = acc[e];
