@@ -186,9 +186,10 @@ int wu_conv3to64_s2_fprop(const float* h1, const float* w, const float* bias, fl
 size_t wu_conv3to64_s2_wgrad_workspace_bytes(int B, int Hin, int Win);
 int wu_conv3to64_s2_wgrad(const float* h1, const void* g, float* dw, float* db, int B, int Hin,
                           int Win, void* workspace, size_t workspace_bytes, wu_stream_t stream);
-/* tcgen05 (N = 16, three live columns) over the four parity classes of g_h1; `workspace` holds the
- * packed bf16 weights (wu_conv3to64_s2_dgrad_workspace_bytes, 128-byte aligned). */
-size_t wu_conv3to64_s2_dgrad_workspace_bytes(void);
+/* "GEMM first, shift afterwards": g is contracted once with all 27 (ci, r, s) weight columns on tcgen05
+ * (a 1x1 convolution into a bf16 scratch tensor), then scattered to (2u + r - 1, 2v + s - 1).  Hin, Win
+ * even; `workspace` (wu_conv3to64_s2_dgrad_workspace_bytes, 128-byte aligned) holds weights + scratch. */
+size_t wu_conv3to64_s2_dgrad_workspace_bytes(int B, int Hin, int Win);
 int wu_conv3to64_s2_dgrad(const void* g, const float* w, float* g_h1, int B, int Hin, int Win,
                           void* workspace, size_t workspace_bytes, wu_stream_t stream);
 /* Backward of the 3->3 convolution: g_x fp32 NCHW (may be NULL: real images / detached fakes need

@@ -52,7 +52,7 @@ SIGNATURES = {
     "wu_conv3to64_s2_fprop": (I, [P, P, P, F, P, I, I, I, P]),
     "wu_conv3to64_s2_wgrad_workspace_bytes": (SZ, [I, I, I]),
     "wu_conv3to64_s2_wgrad": (I, [P, P, P, P, I, I, I, P, SZ, P]),
-    "wu_conv3to64_s2_dgrad_workspace_bytes": (SZ, []),
+    "wu_conv3to64_s2_dgrad_workspace_bytes": (SZ, [I, I, I]),
     "wu_conv3to64_s2_dgrad": (I, [P, P, P, I, I, I, P, SZ, P]),
     "wu_conv3to3_bprop_workspace_bytes": (SZ, []),
     "wu_conv3to3_bprop": (I, [P, P, P, P, P, P, I, I, I, P, SZ, P]),

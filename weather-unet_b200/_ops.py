@@ -279,7 +279,7 @@ class _DiscStem(torch.autograd.Function):
         gx = dw0 = db0 = None
         if need_x or need_w0 or need_b0:
             gh = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
-            nb = query("wu_conv3to64_s2_dgrad_workspace_bytes")
+            nb = query("wu_conv3to64_s2_dgrad_workspace_bytes", B, H, W)
             ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
             call("wu_conv3to64_s2_dgrad", ptr(g), ptr(w1c), ptr(gh), B, H, W, ptr(ws), nb, stream())
             nb = query("wu_conv3to3_bprop_workspace_bytes")

@@ -43,11 +43,6 @@ struct TapParams {
   signed char tap_map[4][9], tap_dx[4][9], tap_dy[4][9], tap_w[4][9];
   float slope;  // epilogue: v > 0 ? v : v * slope   (1 = identity, 0 = ReLU)
   const float* bias;
-  // BN == 16 ("three-channel" mode, dgrad into the discriminator's 3-channel tensor): the first
-  // out_c accumulator columns are written as fp32 NCHW [B][out_c][out_H][out_W] at the parity
-  // position (2u+py, 2v+px) of class (py, px) = (cls_out >> 1, cls_out & 1)
-  float* out_f32;
-  int out_c, out_H, out_W;
 };
 
 template <int BN>
@@ -56,10 +51,9 @@ struct TapCfg {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = BN == 16 ? 0 : 2 * 16384;
+  static constexpr int kStagingBytes = 2 * 16384;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
-  static constexpr int kBufCols = BN == 16 ? 32 : BN;  // TMEM columns between the two accumulators
-  static constexpr uint32_t kTmemCols = 2 * kBufCols;
+  static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
 struct TapTile {
@@ -177,7 +171,7 @@ conv_taps_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ C
         const int buf = it & 1;
         mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * Cfg::kBufCols;
+        const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -198,97 +192,70 @@ conv_taps_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ C
     }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
-    if constexpr (BN == 16) {
-      const int q = warp & 3;
-      const int row = q * 32 + lane;  // pixel within the tile == TMEM lane
-      const int ph = row >> p.log2_bw, pw = row & (p.bw - 1);
-      const long long HW = (long long)p.out_H * p.out_W;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const TapTile t = decode_tap_tile<BN>(p, tile);
-        const int par = p.cls_out[t.cls];
-        mbar_wait(tfull_bar(buf), (it >> 1) & 1);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kBufCols, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(tempty_bar(buf));
-        const int yy = 2 * (t.h0 + ph) + (par >> 1), xx = 2 * (t.w0 + pw) + (par & 1);
-        if (yy < p.out_H && xx < p.out_W) {
-          float* o = p.out_f32 + (long long)t.b * p.out_c * HW + (long long)yy * p.out_W + xx;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c < p.out_c) o[c * HW] = __uint_as_float(v[c]);
-        }
-      }
-    } else {
-      const int q = warp & 3;
-      const int row = q * 32 + lane;  // pixel within the tile == TMEM lane
-      const bool issuer = (threadIdx.x == 64);
-      const float slope = p.slope;
-      const bool act = slope != 1.f;
-      uint32_t store_count = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const TapTile t = decode_tap_tile<BN>(p, tile);
-        const CUtensorMap* dm = &maps.d[p.cls_out[t.cls]];
-        mbar_wait(tfull_bar(buf), (it >> 1) & 1);
-        tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // pixel within the tile == TMEM lane
+    const bool issuer = (threadIdx.x == 64);
+    const float slope = p.slope;
+    const bool act = slope != 1.f;
+    uint32_t store_count = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const TapTile t = decode_tap_tile<BN>(p, tile);
+      const CUtensorMap* dm = &maps.d[p.cls_out[t.cls]];
+      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 64; ++chunk) {
-          uint32_t v[64];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + chunk * 64;
-          tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tmem_ld_wait();
-          if (chunk == BN / 64 - 1) {  // this thread has drained its part of the accumulator
-            tc_fence_before();
-            mbar_arrive(tempty_bar(buf));
-          }
-          const int cbase = t.n0 + chunk * 64;
-          if (p.bias != nullptr) {
+      for (int chunk = 0; chunk < BN / 64; ++chunk) {
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + chunk * 64;
+        tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        if (chunk == BN / 64 - 1) {  // this thread has drained its part of the accumulator
+          tc_fence_before();
+          mbar_arrive(tempty_bar(buf));
+        }
+        const int cbase = t.n0 + chunk * 64;
+        if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-              v[j + 0] = __float_as_uint(__uint_as_float(v[j + 0]) + bv.x);
-              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + bv.y);
-              v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + bv.z);
-              v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + bv.w);
-            }
-          }
-          if (act) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const float f = __uint_as_float(v[j]);
-              v[j] = __float_as_uint(f > 0.f ? f : f * slope);
-            }
-          }
-          uint32_t pk[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          const uint32_t sb = staging_base + (store_count & 1u) * 16384u;
-          ++store_count;
-          if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has read it
-          named_bar_sync(1, 128);
-          uint8_t* srow = smem + (sb - base) + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          fence_proxy_async_smem();
-          named_bar_sync(2, 128);
-          if (issuer) {
-            tma_store_4d(dm, sb, cbase, t.w0, t.h0, t.b);
-            tma_store_commit();
+          for (int j = 0; j < 64; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+            v[j + 0] = __float_as_uint(__uint_as_float(v[j + 0]) + bv.x);
+            v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + bv.y);
+            v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + bv.z);
+            v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + bv.w);
           }
         }
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const float f = __uint_as_float(v[j]);
+            v[j] = __float_as_uint(f > 0.f ? f : f * slope);
+          }
+        }
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        const uint32_t sb = staging_base + (store_count & 1u) * 16384u;
+        ++store_count;
+        if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        named_bar_sync(1, 128);
+        uint8_t* srow = smem + (sb - base) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (issuer) {
+          tma_store_4d(dm, sb, cbase, t.w0, t.h0, t.b);
+          tma_store_commit();
+        }
       }
-      if (issuer) tma_store_wait_all<0>();
     }
+    if (issuer) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -533,13 +500,74 @@ static WgradS2Plan plan_wgrad_s2(int cin, int cout, int B, int Hin, int Win) {
   return pl;
 }
 
-// Conv2d(3, 64, 3, stride 2).weight fp32 [64][3][3][3] -> dgrad B operand bf16 [16][9*64]:
-// row ci (rows 3..15 zero), column (8 - tap) * 64 + co   (same convention as w_dgrad)
-__global__ void pack_w3to64_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 16 * 576; i += gridDim.x * blockDim.x) {
-    const int ci = i / 576, k = i - ci * 576;
-    const int tap = 8 - k / 64, co = k & 63;
-    wd[i] = __float2bfloat16_rn(ci < 3 ? w[(co * 3 + ci) * 9 + tap] : 0.f);
+// ---- data gradient of the 3 -> 64 stride-2 stem convolution: GEMM first, shift afterwards ----------
+// With only three input channels the usual "shift the input, then contract" order wastes the tensor
+// core (N = 3) and re-reads g once per tap.  Here g is contracted ONCE with all 27 (ci, r, s) weight
+// columns, T[b,u,v,(ci,r,s)] = sum_co g[b,u,v,co] * w[co][ci][r][s] (a 1x1 convolution, N = 64 with 27
+// live columns, one pass over g), and a small second kernel scatters T to the output positions
+// (2u + r - 1, 2v + s - 1): every 2x2 block of output pixels reads the four T pixels around it and uses
+// each of their 27 values exactly once.
+__global__ void pack_w3to64_t_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * 64 + co
+  if (i >= 64 * 64) return;
+  const int n = i >> 6, co = i & 63;
+  wt[i] = __float2bfloat16_rn(n < 27 ? w[co * 27 + n] : 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+col2im_s2_kernel(const __nv_bfloat16* __restrict__ T, float* __restrict__ out, int B, int Hin, int Win,
+                 int Ho, int Wo) {
+  const long long nblk = (long long)B * Ho * Wo;
+  const long long HW = (long long)Hin * Win;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblk;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Wo);
+    const long long t = i / Wo;
+    const int Y = (int)(t % Ho);
+    const long long b = t / Ho;
+    float acc[2][2][3];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) acc[dy][dx][ci] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (Y + a >= Ho || X + c >= Wo) continue;
+        const uint4* tp = reinterpret_cast<const uint4*>(T + (((b * Ho + Y + a) * Wo) + X + c) * 64);
+        uint32_t wds[16];  // 32 bf16: the 27 live values of this T pixel
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 v = __ldg(tp + q);
+          wds[4 * q] = v.x; wds[4 * q + 1] = v.y; wds[4 * q + 2] = v.z; wds[4 * q + 3] = v.w;
+        }
+        // tap r lands on output row parity dy = (r + 1) & 1 from T row a = (dy + 1 - r) / 2
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int dy = (r + 1) & 1;
+          if (((dy + 1 - r) >> 1) != a) continue;
+#pragma unroll
+          for (int s3 = 0; s3 < 3; ++s3) {
+            const int dx = (s3 + 1) & 1;
+            if (((dx + 1 - s3) >> 1) != c) continue;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              const int n = ci * 9 + r * 3 + s3;
+              const uint32_t wd = wds[n >> 1];
+              acc[dy][dx][ci] += (n & 1) ? bf16hi(wd) : bf16lo(wd);
+            }
+          }
+        }
+      }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      float* o = out + (b * 3 + ci) * HW + (long long)(2 * Y) * Win + 2 * X;
+      *reinterpret_cast<float2*>(o) = make_float2(acc[0][0][ci], acc[0][1][ci]);
+      if (2 * Y + 1 < Hin) *reinterpret_cast<float2*>(o + Win) = make_float2(acc[1][0][ci], acc[1][1][ci]);
+    }
   }
 }
 
@@ -717,66 +745,59 @@ extern "C" int wu_conv3x3_s2_wgrad(const void* src, int cin, const void* dy, int
 }
 
 // Data gradient of the discriminator stem's Conv2d(3, 64, 3, padding=1, stride=2) (nets.py:30-31 with
-// in_channels = 3): g NHWC bf16 [B][Ho][Wo][64] -> g_h1 fp32 NCHW [B][3][Hin][Win].  Same parity-class
-// decomposition as wu_conv3x3_s2_dgrad with N = 16 accumulator columns (3 live).
-extern "C" size_t wu_conv3to64_s2_dgrad_workspace_bytes(void) { return 16 * 576 * 2; }
+// in_channels = 3): g NHWC bf16 [B][Ho][Wo][64] -> g_h1 fp32 NCHW [B][3][Hin][Win] (Hin, Win even).
+// workspace: packed weights (8 KiB) + T bf16 [B][Ho][Wo][64].
+extern "C" size_t wu_conv3to64_s2_dgrad_workspace_bytes(int B, int Hin, int Win) {
+  if (B <= 0 || Hin <= 0 || Win <= 0) return 0;
+  return 8192 + (size_t)B * ((Hin + 1) / 2) * ((Win + 1) / 2) * 128;
+}
 
 extern "C" int wu_conv3to64_s2_dgrad(const void* g, const float* w, float* g_h1, int B, int Hin,
                                      int Win, void* workspace, size_t workspace_bytes,
                                      wu_stream_t stream) {
   WU_REQUIRE(g && w && g_h1 && workspace, "wu_conv3to64_s2_dgrad: null pointer");
-  WU_REQUIRE(B > 0 && Hin >= 2 && Win >= 2, "wu_conv3to64_s2_dgrad: bad shape B=%d H=%d W=%d", B, Hin, Win);
-  WU_REQUIRE(workspace_bytes >= wu_conv3to64_s2_dgrad_workspace_bytes() &&
+  WU_REQUIRE(B > 0 && Hin >= 2 && Win >= 2 && Hin % 2 == 0 && Win % 2 == 0,
+             "wu_conv3to64_s2_dgrad: bad shape B=%d H=%d W=%d (H, W must be even)", B, Hin, Win);
+  WU_REQUIRE(workspace_bytes >= wu_conv3to64_s2_dgrad_workspace_bytes(B, Hin, Win) &&
                  (reinterpret_cast<uintptr_t>(workspace) & 127) == 0,
              "wu_conv3to64_s2_dgrad: workspace too small or not 128-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  pack_w3to64_dgrad_kernel<<<36, 256, 0, st>>>(w, (__nv_bfloat16*)workspace);
-  WU_CHECK_LAUNCH("pack_w3to64_dgrad_kernel");
-  const int Ho = (Hin + 1) / 2, Wo = (Win + 1) / 2;
+  __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + 8192);
+  pack_w3to64_t_kernel<<<16, 256, 0, st>>>(w, wt);
+  WU_CHECK_LAUNCH("pack_w3to64_t_kernel");
+  const int Ho = Hin / 2, Wo = Win / 2;
   TapParams p{};
   pick_box(Ho, Wo, 128, &p.bw, &p.bh);
   p.log2_bw = ilog2i(p.bw);
   p.c_blocks = 1;
   p.n_tiles = 1;
-  p.n_classes = 4;
-  const int order[4][2] = {{1, 1}, {1, 0}, {0, 1}, {0, 0}};
-  long long total = 0;
-  for (int c = 0; c < 4; ++c) {
-    const int py = order[c][0], px = order[c][1];
-    const int Hv = (Hin - py + 1) / 2, Wv = (Win - px + 1) / 2;
-    p.cls_tw[c] = (Wv + p.bw - 1) / p.bw;
-    p.cls_th[c] = (Hv + p.bh - 1) / p.bh;
-    total += (long long)B * p.cls_tw[c] * p.cls_th[c];
-    WU_REQUIRE(total < (1LL << 31), "wu_conv3to64_s2_dgrad: too many tiles");
-    p.cls_end[c] = (int)total;
-    p.cls_out[c] = py * 2 + px;
-    int n = 0;
-    for (int r = 0; r < 3; ++r) {
-      if (((py + 1 - r) & 1) != 0) continue;
-      for (int s = 0; s < 3; ++s) {
-        if (((px + 1 - s) & 1) != 0) continue;
-        p.tap_map[c][n] = 0;
-        p.tap_dy[c][n] = (signed char)((py + 1 - r) / 2);
-        p.tap_dx[c][n] = (signed char)((px + 1 - s) / 2);
-        p.tap_w[c][n] = (signed char)(8 - (r * 3 + s));
-        ++n;
-      }
-    }
-    p.cls_ntaps[c] = n;
-  }
-  p.num_tiles = (int)total;
+  p.n_classes = 1;
+  p.cls_tw[0] = (Wo + p.bw - 1) / p.bw;
+  p.cls_th[0] = (Ho + p.bh - 1) / p.bh;
+  const long long nt = (long long)B * p.cls_tw[0] * p.cls_th[0];
+  WU_REQUIRE(nt < (1LL << 31), "wu_conv3to64_s2_dgrad: too many tiles");
+  p.num_tiles = (int)nt;
+  p.cls_end[0] = p.num_tiles;
+  p.cls_ntaps[0] = 1;  // a 1x1 convolution: one tap, no shift
+  p.cls_out[0] = 0;
   p.slope = 1.f;
   p.bias = nullptr;
-  p.out_f32 = g_h1;
-  p.out_c = 3;
-  p.out_H = Hin;
-  p.out_W = Win;
   TapMaps maps;
   CUtensorMap bm;
   int rc;
   if ((rc = make_act_tmap(&maps.a[0], g, B, Ho, Wo, 64, 64, p.bw, p.bh)) != WU_OK) return rc;
-  for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
-  for (int i = 0; i < 4; ++i) maps.d[i] = maps.a[0];  // unused in the fp32 NCHW epilogue
-  if ((rc = make_mat_tmap(&bm, workspace, 16, 576, 16)) != WU_OK) return rc;
-  return launch_taps<16>(maps, bm, p, st);
+  if ((rc = make_act_tmap(&maps.d[0], T, B, Ho, Wo, 64, 64, p.bw, p.bh)) != WU_OK) return rc;
+  for (int i = 1; i < 4; ++i) {
+    maps.a[i] = maps.a[0];
+    maps.d[i] = maps.d[0];
+  }
+  if ((rc = make_mat_tmap(&bm, wt, 64, 64, 64)) != WU_OK) return rc;
+  if ((rc = launch_taps<64>(maps, bm, p, st)) != WU_OK) return rc;
+  const long long nblk = (long long)B * Ho * Wo;
+  long long grid = (nblk + 255) / 256;
+  if (grid > 148LL * 32) grid = 148LL * 32;
+  col2im_s2_kernel<<<(int)grid, 256, 0, st>>>(T, g_h1, B, Hin, Win, Ho, Wo);
+  WU_CHECK_LAUNCH("col2im_s2_kernel");
+  return WU_OK;
 }
