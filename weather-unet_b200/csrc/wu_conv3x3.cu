@@ -1260,22 +1260,23 @@ bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict
     partial[(size_t)blockIdx.x * C + c] = s;
   }
 }
-// db[c] = sum_b partial[b][c]: one block per 32 channels, 8 threads share a channel's block range
+// db[c] = sum_b partial[b][c]: one block per 8 channels, 32 threads share a channel's row range
+// (rows = 4 x splits <= 592: a longer chain per thread made this a 10 us kernel for 64 channels)
 __global__ void __launch_bounds__(256)
 bias_grad_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int nblocks,
                        int C) {
-  __shared__ float red[8][32];
-  const int cl = threadIdx.x & 31, part = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ float red[32][8];
+  const int cl = threadIdx.x & 7, part = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   float s = 0.f;
   if (c < C)
-    for (int b = part; b < nblocks; b += 8) s += partial[(size_t)b * C + c];
+    for (int b = part; b < nblocks; b += 32) s += partial[(size_t)b * C + c];
   red[part][cl] = s;
   __syncthreads();
   if (part == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][cl];
+    for (int i = 0; i < 32; ++i) t += red[i][cl];
     db[c] = t;
   }
 }
@@ -1580,7 +1581,7 @@ int wgrad_fold(const float* partial, int splits, int cin, int cout, float* dw, c
     bias_grad_partial_kernel<<<kBiasGradBlocks, 256, groups * cout * sizeof(float), st>>>(
         (const __nv_bfloat16*)dy, bias_scratch, npix, cout);
     WU_CHECK_LAUNCH("bias_grad_partial_kernel");
-    bias_grad_final_kernel<<<(cout + 31) / 32, 256, 0, st>>>(bias_scratch, db, kBiasGradBlocks, cout);
+    bias_grad_final_kernel<<<(cout + 7) / 8, 256, 0, st>>>(bias_scratch, db, kBiasGradBlocks, cout);
     WU_CHECK_LAUNCH("bias_grad_final_kernel");
   }
   return WU_OK;
@@ -1651,7 +1652,7 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     if ((rc = wgrad_fold(q.partial, pl.splits, cin, cout, dw, dy, 0, nullptr, nullptr, st)) != WU_OK)
       return rc;
     if (db != nullptr) {  // fold the in-kernel column sums: [4 * splits][cout] -> db
-      bias_grad_final_kernel<<<(cout + 31) / 32, 256, 0, st>>>(bscratch, db, 4 * pl.splits, cout);
+      bias_grad_final_kernel<<<(cout + 7) / 8, 256, 0, st>>>(bscratch, db, 4 * pl.splits, cout);
       WU_CHECK_LAUNCH("bias_grad_final_kernel");
     }
     return WU_OK;
