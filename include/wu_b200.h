@@ -255,6 +255,16 @@ int wu_sn_backward(const void* tensors, const void* dot_chunks, int n_dot_chunks
 int wu_adam_multi(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, wu_stream_t stream);
 
+/* ---- per-sample L1 distance (t_cls_train.py:255,259-266; ops.py:22-24) ------------
+ * d[s] = mean_i |a[s][i] - b[s][i]| over the n elements of sample s (fp32, contiguous), one pass; the
+ * generator loss terms g_loss_l1 = mean_s d[s] and loss_con = mean_s d[s] / (lambda_s + eps) follow
+ * from it.  Backward: ga[s][i] = sign(a - b) * gd[s] / n.  n %% 4 == 0, 16-byte aligned pointers. */
+size_t wu_l1_per_sample_workspace_bytes(int B);
+int wu_l1_per_sample_fwd(const float* a, const float* b, float* d, int B, long long n, void* workspace,
+                         size_t workspace_bytes, wu_stream_t stream);
+int wu_l1_per_sample_bwd(const float* a, const float* b, const float* gd, float* ga, int B, long long n,
+                         wu_stream_t stream);
+
 /* ---- layout helpers (tests, interop with NCHW fp32 PyTorch tensors) ---------------------------*/
 int wu_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W,
                              wu_stream_t stream);

@@ -209,3 +209,21 @@ def test_disc_stem_kernels(cuda):
     mine2 = [x.clone()] + [t.clone().requires_grad_(True) for t in (w0, b0, w1, b1)]
     K.disc_stem(*mine2, 0.2).backward(gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
     assert torch.allclose(mine2[1].grad, mine[1].grad) and torch.allclose(mine2[3].grad, mine[3].grad)
+
+
+def test_l1_per_sample(cuda):
+    """wu_l1_per_sample_* (t_cls_train.py:255,259-266) against the PyTorch expression, value and
+    gradient."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator().manual_seed(3)
+    a = (torch.rand(5, 3, 24, 40, generator=g) * 2 - 1).to(cuda).requires_grad_(True)
+    b = (torch.rand(5, 3, 24, 40, generator=g) * 2 - 1).to(cuda)
+    w = torch.rand(5, generator=g).to(cuda)
+    ref = (a - b).abs().mean(dim=(1, 2, 3))
+    (ref * w).sum().backward()
+    g_ref, a.grad = a.grad, None
+    assert K.l1_per_sample_supported(a, b)
+    d = K.l1_per_sample(a, b)
+    assert torch.allclose(d, ref, rtol=1e-5, atol=1e-7)
+    (d * w).sum().backward()
+    assert torch.allclose(a.grad, g_ref, rtol=1e-6, atol=1e-9)

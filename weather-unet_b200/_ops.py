@@ -396,6 +396,40 @@ def disc_block(x, w0, b0, w1, b1, slope):
     return _DiscBlock.apply(x, w0, b0, w1, b1, slope)
 
 
+class _L1PerSample(torch.autograd.Function):
+    """d[s] = mean |a[s] - b[s]| per sample in one pass (and one pass backward, gradient w.r.t. `a`)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        B = a.shape[0]
+        n = a[0].numel()
+        d = torch.empty((B,), dtype=torch.float32, device=a.device)
+        nb = query("wu_l1_per_sample_workspace_bytes", B)
+        ws = torch.empty((nb,), dtype=torch.uint8, device=a.device)
+        call("wu_l1_per_sample_fwd", ptr(a), ptr(b), ptr(d), B, n, ptr(ws), nb, stream())
+        ctx.save_for_backward(a, b)
+        return d
+
+    @staticmethod
+    def backward(ctx, gd):
+        a, b = ctx.saved_tensors
+        ga = torch.empty_like(a)
+        call("wu_l1_per_sample_bwd", ptr(a), ptr(b), ptr(gd.contiguous().float()), ptr(ga), a.shape[0],
+             a[0].numel(), stream())
+        return ga, None
+
+
+def l1_per_sample_supported(a, b):
+    return (a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32
+            and a.shape == b.shape and a.is_contiguous() and b.is_contiguous() and not b.requires_grad
+            and a[0].numel() % 4 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
+
+
+def l1_per_sample(a, b):
+    """mean over all but the batch dimension of |a - b| (gradient flows to `a` only)."""
+    return _L1PerSample.apply(a, b)
+
+
 def nchw_to_nhwc(x):
     """fp32 NCHW -> bf16 NHWC."""
     B, C, H, W = x.shape

@@ -14,6 +14,11 @@ import torch.nn.functional as F
 from .ops import dis_hinge, gen_hinge, l1_loss
 
 
+def _ops():
+    from . import _ops as K  # deferred: the ctypes library is only needed on a GPU
+    return K
+
+
 class GradBuckets:
     """Flat fp32 gradient buckets with `param.grad` as views into them (no copies), all-reduced
     (sum / world) bucket by bucket on a side stream as soon as every gradient of a bucket has been
@@ -202,8 +207,12 @@ class GDTrainStep:
             fake_img = shared if self.share_fake else G(images, c_target, dropout_masks=masks_g)
             fake = self._disc(fake_img, c_target)
             g_adv = gen_hinge(fake)
-            g_l1 = l1_loss(fake_img, images)  # logged only (:255)
-            diff = (fake_img - images).abs().mean(dim=(1, 2, 3))
+            if images.is_cuda and _ops().l1_per_sample_supported(fake_img, images):
+                diff = _ops().l1_per_sample(fake_img, images)  # one pass each way (wu_l1_per_sample_*)
+                g_l1 = diff.detach().mean()  # == F.l1_loss (equal sample sizes); logged only (:255)
+            else:
+                g_l1 = l1_loss(fake_img, images)  # logged only (:255)
+                diff = (fake_img - images).abs().mean(dim=(1, 2, 3))
             lmda = (c_real - c_target).abs().mean(dim=1)
             loss_con = (diff / (lmda + self.eps_con)).mean()
             g_loss = g_adv + loss_con
