@@ -320,6 +320,11 @@ def run_ours(args):
         # ---- roofline of the dominant kernel family, timed alone with CUDA events on this stream:
         # the implicit-GEMM convolution at the generator's largest layer (dconv_up1.0: 192 -> 64 at
         # full resolution, 14.5 GFLOP per image forward), inputs far larger than L2
+        # the kernels below are "timed alone" against the BURST peak: let the board leave the power-capped
+        # state the training loop put it in (MEASURED_PEAKS' burst figure was taken from idle as well)
+        torch.cuda.synchronize()
+        time.sleep(2.0)
+
         def time_ms(fn, it=10):
             for _ in range(3):
                 fn()
