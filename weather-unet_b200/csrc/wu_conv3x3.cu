@@ -718,16 +718,6 @@ static int conv_impl() {
   return v;
 }
 
-// WU_CONV_2SM=1: the N = 64 single-source layers on CTA pairs (wu_conv3x3_2sm.cu); read once.
-static int conv_2sm() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WU_CONV_2SM");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 static int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -1422,8 +1412,6 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
   WU_REQUIRE(cout > 0 && cout % 64 == 0 && cout != 192 && (cout <= 256 || cout % 256 == 0),
              "wu_conv3x3_fprop: cout=%d must be 64, 128 or a multiple of 256", cout);
   const int bn = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
-  if (bn == 64 && c1 == 0 && conv_2sm())
-    return conv3x3_2sm(src0, c0, w_packed, bias, relu, relu_mask_src, dst, B, H, W, (cudaStream_t)stream);
   if (conv_impl() == 2 || (conv_impl() == 0 && bn < 256)) {
     const int T = bn == 64 ? 4 : (bn == 128 ? 2 : 1);
     ConvParams2 q;

@@ -69,10 +69,6 @@ size_t conv_k27_wgrad_tc_workspace_bytes();
 int conv_k27_wgrad_tc(const float* x, const void* dy, float* dw, float* db, int B, int Hin, int Win,
                       int stride, void* workspace, cudaStream_t st);
 
-// N = 64 convolution on CTA pairs (tcgen05.mma.cta_group::2); single source.  wu_conv3x3_2sm.cu.
-int conv3x3_2sm(const void* src, int cin, const void* w_packed, const float* bias, int relu,
-                const void* relu_mask_src, void* dst, int B, int H, int W, cudaStream_t st);
-
 // Launch accounting behind wu_launch_count().
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
