@@ -1327,6 +1327,7 @@ static WgradPlan plan_wgrad(int cin_total, int cout, int B, int H, int W) {
     if (splits > pl.pix_tiles) splits = pl.pix_tiles;
     if (splits < 1) splits = 1;
     if (splits > num_sms()) splits = num_sms();
+    if (splits > kBiasGradBlocks / 4) splits = kBiasGradBlocks / 4;  // in-kernel bias sums: 4 rows per split
     pl.splits = splits;
     pl.partial_bytes = (size_t)splits * 9 * cin_total * cout * sizeof(float);
     pl.bias_blocks = kBiasGradBlocks;
