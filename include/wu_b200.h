@@ -228,7 +228,9 @@ int wu_conv3x3_s2_wgrad(const void* src, int cin, const void* dy, int cout, int 
  *   v <- normalize(W^T u), u <- normalize(W v), sigma = u . (W v), W_sn = W / sigma   (eps on the norms);
  * eval mode (training == 0) uses the stored u, v.  `tensors`: device array of records
  *   {const float* w; float* u; float* v; float* u_snap; float* v_snap; float* sigma; float* t; float* s;
- *    float* part; float* w_sn; const float* g; float* dw; int32 rows; int32 cols}          (104 bytes)
+ *    float* part; float* w_sn; const float* g; float* dw; bf16* wf; bf16* wd; int32 rows; int32 cols}
+ * (120 bytes).  wf / wd non-NULL (3x3 convolution weights, cols = 9 * cin): W / sigma is written
+ * directly in the packed operand layouts of wu_pack_conv3x3_weights and w_sn is left untouched;
  * with t [cols], s [rows], part [wu_sn_parts()] scratch; u_snap / v_snap / sigma are this forward's
  * values, kept for the backward pass.  Work items {int32 tensor; int32 begin; int32 count; int32 index}:
  *   wtu_chunks : begin = first column, wu_sn_wtu_cols() columns each, index = chunk number in its tensor

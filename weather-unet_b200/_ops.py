@@ -342,14 +342,17 @@ class _DiscBlock(torch.autograd.Function):
     their gradients flow back into the spectral-norm graph (weight_orig, sigma) on the torch side."""
 
     @staticmethod
-    def forward(ctx, x, w0, b0, w1, b1, slope):
+    def forward(ctx, x, w0, b0, w1, b1, slope, packed):
         xn = x.permute(0, 2, 3, 1)  # NHWC view of channels_last memory
         if xn.dtype != BF16 or not xn.is_contiguous():
             xn = xn.to(BF16).contiguous()
         B, H, W, cin = xn.shape
         cout = w1.shape[0]
-        w0f, w0d = pack_conv3x3_weights(w0.detach().float().contiguous())
-        w1f, w1d = pack_conv3x3_weights(w1.detach().float().contiguous())
+        if packed is not None:  # bf16 operand layouts written by the fused spectral norm (w0 / w1
+            (w0f, w0d), (w1f, w1d) = packed  # are autograd handles only)
+        else:
+            w0f, w0d = pack_conv3x3_weights(w0.detach().float().contiguous())
+            w1f, w1d = pack_conv3x3_weights(w1.detach().float().contiguous())
         h = conv3x3(xn, None, w0f, b0.detach().float(), False, None, cin)  # no activation (nets.py:28-29)
         y = conv3x3_s2(h, w1f, b1.detach().float(), slope, cout)
         ctx.save_for_backward(xn, h, y, w0d, w1d)
@@ -381,7 +384,7 @@ class _DiscBlock(torch.autograd.Function):
             if need_x:
                 gx = conv3x3(gh, None, w0d, None, False, None, cin).permute(0, 3, 1, 2)
         return (gx, dw0 if need_w0 else None, db0 if need_b0 else None, dw1,
-                db1 if need_b1 else None, None)
+                db1 if need_b1 else None, None, None)
 
 
 def disc_block_supported(x):
@@ -392,8 +395,10 @@ def disc_block_supported(x):
             and x.is_contiguous(memory_format=torch.channels_last))
 
 
-def disc_block(x, w0, b0, w1, b1, slope):
-    return _DiscBlock.apply(x, w0, b0, w1, b1, slope)
+def disc_block(x, w0, b0, w1, b1, slope, packed=None):
+    """packed: ((w0_fprop, w0_dgrad), (w1_fprop, w1_dgrad)) when the caller already holds the bf16
+    operand layouts of the two weights (then w0 / w1 only carry the autograd graph)."""
+    return _DiscBlock.apply(x, w0, b0, w1, b1, slope, packed)
 
 
 class _L1PerSample(torch.autograd.Function):

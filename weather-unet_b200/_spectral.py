@@ -11,6 +11,9 @@ import torch
 from ._lib import call, query, stream
 
 
+_REC = "<QQQQQQQQQQQQQQii"  # one SnTensor record of csrc/wu_spectral.cu (14 pointers, rows, cols)
+
+
 def _upload(buf, dev):
     return torch.frombuffer(bytearray(buf), dtype=torch.uint8).pin_memory().to(dev, non_blocking=True)
 
@@ -91,9 +94,26 @@ class FusedSpectralNorm:
             t = self._tables[key] = _upload(b"".join(records), dev)
         return t
 
+    def packs(self, i):
+        """True when weight i is a 3x3 convolution the tcgen05 kernels take (packed bf16 output)."""
+        w = self.modules[i].weight_orig
+        return w.dim() == 4 and tuple(w.shape[2:]) == (3, 3) and w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0
+
     def __call__(self, training):
-        """-> list of W / sigma (fp32, weight_orig's shape), one per module."""
-        return list(_SNAll.apply(self, bool(training), *[m.weight_orig for m in self.modules]))
+        """-> (ws, packed): ws[i] = W / sigma (fp32, weight_orig's shape; for the packed 3x3 convolution
+        weights only an autograd handle whose values are NOT written), packed[i] = (w_fprop, w_dgrad)
+        bf16 operand layouts or None."""
+        n = len(self.modules)
+        outs = _SNAll.apply(self, bool(training), *[m.weight_orig for m in self.modules])
+        ws, extra = list(outs[:n]), list(outs[n:])
+        packed, k = [], 0
+        for i in range(n):
+            if self.packs(i):
+                packed.append((extra[k], extra[k + 1]))
+                k += 2
+            else:
+                packed.append(None)
+        return ws, packed
 
 
 class _SNAll(torch.autograd.Function):
@@ -112,15 +132,23 @@ class _SNAll(torch.autograd.Function):
         t_o, s_o = vs_o + cols_tot, vs_o + 2 * cols_tot
         p_o = s_o + rows_tot
         outs = [torch.empty_like(w) for w in ws]
+        extra = []
         recs, ro, co = [], 0, 0
         base = buf.data_ptr()
         for i, (m, w, o) in enumerate(zip(sn.modules, ws, outs)):
             rows, cols = sn.shapes[i]
+            wf = wd = 0
+            if sn.packs(i):
+                cin = w.shape[1]
+                tf = torch.empty((rows, 9 * cin), dtype=torch.bfloat16, device=dev)
+                td = torch.empty((cin, 9 * rows), dtype=torch.bfloat16, device=dev)
+                extra += [tf, td]
+                wf, wd = tf.data_ptr(), td.data_ptr()
             recs.append(struct.pack(
-                "<QQQQQQQQQQQQii", w.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
+                _REC, w.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
                 base + 4 * (us_o + ro), base + 4 * (vs_o + co), base + 4 * (sig_o + i),
                 base + 4 * (t_o + co), base + 4 * (s_o + ro), base + 4 * (p_o + i * nparts),
-                o.data_ptr(), 0, 0, rows, cols))
+                o.data_ptr(), 0, 0, wf, wd, rows, cols))
             ro += rows
             co += cols
         key = ("fwd", training) + tuple(r for r in recs)
@@ -130,11 +158,14 @@ class _SNAll(torch.autograd.Function):
             call("wu_sn_forward", table.data_ptr(), nt, st["wtu"].data_ptr(), n[0], st["wv"].data_ptr(),
                  n[1], st["elem"].data_ptr(), n[2], int(training), sn.eps, stream())
         ctx.sn, ctx.buf, ctx.recs = sn, buf, recs
+        ctx.n = nt
         ctx.save_for_backward(*ws)
-        return tuple(outs)
+        ctx.mark_non_differentiable(*extra)
+        return tuple(outs) + tuple(extra)
 
     @staticmethod
     def backward(ctx, *grads):
+        grads = grads[:ctx.n]  # the packed bf16 copies are not differentiable
         sn, ws = ctx.sn, ctx.saved_tensors
         dev = ws[0].device
         st = sn._static_chunks(dev)
@@ -143,13 +174,13 @@ class _SNAll(torch.autograd.Function):
             return (None, None) + tuple(None for _ in ws)
         recs, keep, dws = [], [], [None] * len(ws)
         for i, rec in enumerate(ctx.recs):
-            f = list(struct.unpack("<QQQQQQQQQQQQii", rec))
+            f = list(struct.unpack(_REC, rec))
             if i in live:
                 g = grads[i].contiguous().float()
                 keep.append(g)
                 dws[i] = torch.empty_like(ws[i])
                 f[10], f[11] = g.data_ptr(), dws[i].data_ptr()
-            recs.append(struct.pack("<QQQQQQQQQQQQii", *f))
+            recs.append(struct.pack(_REC, *f))
         table = sn._table(("bwd",) + tuple(recs), recs, dev)
         if len(live) == len(ws):
             dot, nd, bw, nb = st["dot"], st["n"][3], st["bwd"], st["n"][4]

@@ -14,11 +14,13 @@
 // exactly what autograd does for the reference) is
 //     dW = G / sigma - (<G, W> / sigma^2) u v^T :  sn_dot (partial <G, W>)  ->  sn_bwd.
 // Everything is fp32, like the reference.
+#include <cuda_bf16.h>
+
 #include "wu_host.h"
 
 namespace wu {
 
-struct SnTensor {   // one record of the device-side table (13 x 8 bytes)
+struct SnTensor {   // one record of the device-side table (14 x 8 + 8 bytes)
   const float* w;   // [rows][cols] weight_orig
   float* u;         // [rows] weight_u (updated in place in training mode)
   float* v;         // [cols] weight_v
@@ -31,6 +33,10 @@ struct SnTensor {   // one record of the device-side table (13 x 8 bytes)
   float* w_sn;      // [rows][cols] W / sigma
   const float* g;   // backward: gradient w.r.t. w_sn
   float* dw;        // backward: gradient w.r.t. w
+  // 3x3 convolution weights that feed the tcgen05 kernels: W / sigma goes straight into the packed bf16
+  // operand layouts of wu_pack_conv3x3_weights (w_sn is then not written); null otherwise
+  __nv_bfloat16* wf;  // [rows][9 * cin], k = tap * cin + ci
+  __nv_bfloat16* wd;  // [cin][9 * rows], k = (8 - tap) * rows + co
   int rows, cols;
 };
 struct SnChunk {  // work item
@@ -176,7 +182,19 @@ sn_scale_kernel(const SnTensor* __restrict__ tensors, const SnChunk* __restrict_
   const float sig = T.sigma[0];
   const size_t n = (size_t)T.rows * T.cols;
   const size_t e0 = (size_t)ck.begin * 1024, e1 = min(n, e0 + (size_t)ck.count * 1024);
-  for (size_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) T.w_sn[i] = T.w[i] / sig;
+  if (T.wf == nullptr) {
+    for (size_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) T.w_sn[i] = T.w[i] / sig;
+    return;
+  }
+  const int cout = T.rows, cin = T.cols / 9;
+  for (size_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) {  // i = (co * cin + ci) * 9 + tap
+    const int tap = (int)(i % 9);
+    const size_t cc = i / 9;
+    const int ci = (int)(cc % cin), co = (int)(cc / cin);
+    const __nv_bfloat16 v = __float2bfloat16_rn(T.w[i] / sig);
+    T.wf[(size_t)co * T.cols + (size_t)tap * cin + ci] = v;
+    T.wd[(size_t)ci * 9 * cout + (size_t)(8 - tap) * cout + co] = v;
+  }
 }
 
 // backward, step 1: part[index] = sum over the chunk of g * w

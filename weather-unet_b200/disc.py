@@ -120,7 +120,7 @@ class SNDisc(nn.Module):
         if not sn.supported():
             return None
         with torch.autocast("cuda", enabled=False):
-            ws = sn(self.training)  # W / sigma of all ten weights, fp32 like the reference
+            ws, packed = sn(self.training)  # W / sigma of all ten weights, fp32 like the reference
             slope = self.conv1[2].negative_slope
             h = K.disc_stem(x, ws[0], self.conv1[0].bias, ws[1], self.conv1[1].bias, slope)
             feats = [h]
@@ -129,7 +129,7 @@ class SNDisc(nn.Module):
                 if not K.disc_block_supported(h):
                     return None
                 h = K.disc_block(h, ws[2 * i - 2], blk[0].bias, ws[2 * i - 1], blk[1].bias,
-                                 blk[2].negative_slope)
+                                 blk[2].negative_slope, packed=(packed[2 * i - 2], packed[2 * i - 1]))
                 feats.append(h)
             pooled = h.sum(dim=(2, 3), dtype=torch.float32)  # global SUM pool (disc.py:32)
             out = F.linear(pooled, ws[8], self.l.bias)
