@@ -1218,6 +1218,42 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// Same, and the blocks past `main_blocks` fold the in-kernel bias partials (rows x cout) into db:
+// one launch instead of two for every convolution's weight + bias gradient.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_bias_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int cin,
+                         int cout, int main_blocks, const float* __restrict__ bias_partial, int rows,
+                         float* __restrict__ db) {
+  if ((int)blockIdx.x < main_blocks) {
+    const long long total = 9LL * cin * cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)main_blocks * blockDim.x) {
+      const int co = (int)(i % cout);
+      const long long rc = i / cout;
+      const int ci = (int)(rc % cin);
+      const int tap = (int)(rc / cin);
+      float acc = 0.f;
+      for (int z = 0; z < splits; ++z) acc += partial[z * total + i];
+      dw[((long long)co * cin + ci) * 9 + tap] = acc;
+    }
+    return;
+  }
+  __shared__ float red[32][8];
+  const int cl = threadIdx.x & 7, part = threadIdx.x >> 3;
+  const int c = ((int)blockIdx.x - main_blocks) * 8 + cl;
+  float sum = 0.f;
+  if (c < cout)
+    for (int b = part; b < rows; b += 32) sum += bias_partial[(size_t)b * cout + c];
+  red[part][cl] = sum;
+  __syncthreads();
+  if (part == 0 && c < cout) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][cl];
+    db[c] = t;
+  }
+}
+
 // db[c] = sum_p dy[p][c]; stage 1: per-block partial sums (deterministic), stage 2: fold.
 __global__ void __launch_bounds__(256)
 bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial,
@@ -1650,11 +1686,14 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     else if (pl.bn == 64) rc = launch_wgrad2<64, 5>(x0, x1, ym, q, grid, st);
     else rc = launch_wgrad2<128, 2>(x0, x1, ym, q, grid, st);
     if (rc != WU_OK) return rc;
-    if ((rc = wgrad_fold(q.partial, pl.splits, cin, cout, dw, dy, 0, nullptr, nullptr, st)) != WU_OK)
-      return rc;
-    if (db != nullptr) {  // fold the in-kernel column sums: [4 * splits][cout] -> db
-      bias_grad_final_kernel<<<(cout + 7) / 8, 256, 0, st>>>(bscratch, db, 4 * pl.splits, cout);
-      WU_CHECK_LAUNCH("bias_grad_final_kernel");
+    if (db == nullptr) return wgrad_fold(q.partial, pl.splits, cin, cout, dw, dy, 0, nullptr, nullptr, st);
+    {  // split-K fold + fold of the in-kernel column sums ([4 * splits][cout] -> db), one launch
+      const long long total = 9LL * cin * cout;
+      int gmain = (int)((total + 255) / 256);
+      if (gmain > 148 * 16) gmain = 148 * 16;
+      wgrad_reduce_bias_kernel<<<gmain + (cout + 7) / 8, 256, 0, st>>>(q.partial, dw, pl.splits, cin, cout,
+                                                                      gmain, bscratch, 4 * pl.splits, db);
+      WU_CHECK_LAUNCH("wgrad_reduce_bias_kernel");
     }
     return WU_OK;
   }
