@@ -71,7 +71,7 @@ def test_golden_eval_and_train(cuda):
 
 
 @pytest.mark.parametrize("B,H,W,nc,train", [(2, 64, 64, 5, True), (1, 32, 96, 6, True),
-                                            (3, 64, 32, 5, False)])
+                                            (3, 64, 32, 5, False), (1, 256, 256, 5, True)])
 def test_against_oracle(cuda, B, H, W, nc, train):
     from oracle import cunet_oracle as orc
     net = make_net(nc, seed=3).to(cuda)
