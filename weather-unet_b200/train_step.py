@@ -195,16 +195,20 @@ class GDTrainStep:
         fake = self._disc(fake_img, c_target)
         d_loss = dis_hinge(fake, real)
         d_loss.backward()
+        # ---- generator update (t_cls_train.py:226-286)
+        self._zero(self.g_opt, self.g_buckets)
+        # The generator's forward does not read the discriminator, so it is enqueued BEFORE the
+        # discriminator's gradient all-reduce is awaited and its Adam step applied: in data-parallel
+        # runs the reduction (one bucket that completes at the very end of D's backward) hides under
+        # the generator's convolutions.  Same arithmetic, same order of updates as the reference.
+        fake_img = shared if self.share_fake else G(images, c_target, dropout_masks=masks_g)
         if self.d_buckets is not None:
             self.d_buckets.finish()
         self.d_opt.step()
-        # ---- generator update (t_cls_train.py:226-286)
-        self._zero(self.g_opt, self.g_buckets)
         d_params = [p for p in D.parameters()]
         for p in d_params:  # D's weight gradients of this pass are discarded by the reference
             p.requires_grad_(False)
         try:
-            fake_img = shared if self.share_fake else G(images, c_target, dropout_masks=masks_g)
             fake = self._disc(fake_img, c_target)
             g_adv = gen_hinge(fake)
             if images.is_cuda and _ops().l1_per_sample_supported(fake_img, images):
