@@ -622,11 +622,11 @@ __device__ __forceinline__ uint4 keep_mask8(uint32_t thr, uint64_t seed,
 }
 
 // grid = (ceil(2w * C/8 / 256), B * ceil(2h / kRowsPerThread)): a thread produces kRowsPerThread
-// consecutive output rows of its (column, 8-channel vector), so 32 independent 16-byte loads are in
+// consecutive output rows of its (column, 8-channel vector), so 16 independent 16-byte loads are in
 // flight per thread.  The kernel is instruction bound (RNG + interpolation per 16 output bytes), so
-// the dropout mode is a template parameter and all row-invariant index math is hoisted; 8 rows
-// (121 registers, two blocks per SM) amortise it best: 4 rows were 15 % slower, 16 rows 35 %.
-constexpr int kRowsPerThread = 8;
+// the dropout mode is a template parameter and all row-invariant index math is hoisted.  (8 rows per
+// thread: same time under ncu, 121 registers; 16 rows: 35 % slower.)
+constexpr int kRowsPerThread = 4;
 template <int MODE>
 __global__ void __launch_bounds__(256)
 adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
@@ -902,28 +902,43 @@ __global__ void __launch_bounds__(256)
 adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ gz, const __nv_bfloat16* __restrict__ x,
                        const float* __restrict__ coef, __nv_bfloat16* __restrict__ gx, int B, int HW,
                        int C) {
+  // blockIdx.y = image: a thread keeps the 24 coefficients of its 8 channels in registers and walks
+  // the image's pixels four at a time (eight independent 16-byte loads in flight)
   const int cv = C >> 3;
-  const long long total = (long long)B * HW * cv;
+  const int b = blockIdx.y;
+  const int l = threadIdx.x % cv, grp = threadIdx.x / cv, groups = blockDim.x / cv;
   const size_t plane = (size_t)B * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cv);
-    const int b = (int)(i / ((long long)HW * cv));
-    const float4* cp = reinterpret_cast<const float4*>(coef + (size_t)b * C + v * 8);
-    const float4 a0 = __ldg(cp), a1 = __ldg(cp + 1);
-    const float4 b0 = __ldg(cp + plane / 4), b1 = __ldg(cp + plane / 4 + 1);
-    const float4 c0 = __ldg(cp + plane / 2), c1 = __ldg(cp + plane / 2 + 1);
-    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float Bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float Cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const float4* cp = reinterpret_cast<const float4*>(coef + (size_t)b * C + l * 8);
+  const float4 a0 = __ldg(cp), a1 = __ldg(cp + 1);
+  const float4 b0 = __ldg(cp + plane / 4), b1 = __ldg(cp + plane / 4 + 1);
+  const float4 c0 = __ldg(cp + plane / 2), c1 = __ldg(cp + plane / 2 + 1);
+  const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float Bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float Cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const size_t img = (size_t)b * HW * C + l * 8;
+  const int stride = gridDim.x * groups;
+  auto one = [&](const uint4& gq, const uint4& xq, int p) {
     float g[8], xv[8], o[8];
-    unpack8(ld_stream16(gz + i * 8), g);
-    unpack8(ld_stream16(x + i * 8), xv);
+    unpack8(gq, g);
+    unpack8(xq, xv);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       o[j] = xv[j] > 0.f ? fmaf(A[j], g[j], fmaf(Bc[j], xv[j], Cc[j])) : 0.f;
-    st_stream16(gx + i * 8, pack8(o));
+    st_stream16(gx + img + (size_t)p * C, pack8(o));
+  };
+  int p = blockIdx.x * groups + grp;
+  for (; p + 3 * stride < HW; p += 4 * stride) {
+    uint4 gq[4], xq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      gq[u] = ld_stream16(gz + img + (size_t)(p + u * stride) * C);
+      xq[u] = ld_stream16(x + img + (size_t)(p + u * stride) * C);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(gq[u], xq[u], p + u * stride);
   }
+  for (; p < HW; p += stride)
+    one(ld_stream16(gz + img + (size_t)p * C), ld_stream16(x + img + (size_t)p * C), p);
 }
 
 static inline int grid_for(long long work_items, int block, int max_waves = 16) {
@@ -1172,8 +1187,14 @@ extern "C" int wu_adain_bwd_apply(const void* gz, const void* x, const float* co
                                   int HW, int C, wu_stream_t stream) {
   WU_REQUIRE(gz && x && coef && gx && B > 0 && HW > 0, "wu_adain_bwd_apply: bad args");
   WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_bwd_apply: C=%d must be a multiple of 8", C);
-  const long long total = (long long)B * HW * (C / 8);
-  adain_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  WU_REQUIRE(B <= 65535 && C <= 2048 && 256 % (C / 8) == 0,
+             "wu_adain_bwd_apply: B=%d / C=%d outside the kernel's decomposition", B, C);
+  const int groups = 256 / (C / 8);
+  int bx = (HW + groups * 4 - 1) / (groups * 4);  // four pixels per thread and iteration
+  const int cap = (148 * 16 + B - 1) / B;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  adain_bwd_apply_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)gz, (const bf16*)x, coef, (bf16*)gx, B, HW, C);
   WU_CHECK_LAUNCH("adain_bwd_apply_kernel");
   return WU_OK;
