@@ -182,3 +182,16 @@ def test_checkpoint_roundtrip_with_reference_format(tmp_path):
     assert ck.load_checkpoint(ref_path, Conditional_UNet(5)) == (7, 99)
     with pytest.raises(RuntimeError):
         ck.load_checkpoint(ref_path, Conditional_UNet(6))  # strict, like the reference
+
+
+def test_spectral_norm_record_layout():
+    """The pointer-table record _spectral.py packs must be the 120-byte SnTensor of csrc/wu_spectral.cu
+    (14 pointers + rows + cols) that include/wu_b200.h documents."""
+    import struct
+    from weather_unet_b200 import _spectral
+    assert struct.calcsize(_spectral._REC) == 120
+    src = open(os.path.join(ROOT, "weather-unet_b200", "csrc", "wu_spectral.cu")).read()
+    body = src[src.index("struct SnTensor {"):src.index("};", src.index("struct SnTensor {"))]
+    members = re.findall(r"^\s*(?:const )?\w+\* \w+;", body, flags=re.M)
+    assert len(members) == 14 and "int rows, cols;" in body, members
+    assert "(120 bytes)" in open(os.path.join(ROOT, "include", "wu_b200.h")).read()
