@@ -78,9 +78,14 @@ class Trainer:
         self.d_opt = torch.optim.Adam([v for v in self.d.values() if v.requires_grad], lr=lr,
                                       betas=(0.0, 0.999), weight_decay=lr / 20)
 
-    def step(self, images, c_real, c_target, masks_d=None, masks_g=None, train=True):
+    def step(self, images, c_real, c_target, masks_d=None, masks_g=None, train=True,
+             estimator=None, eps_con=1e-2):
         """One iteration: D update then G update.  Returns dict of the losses.
-        masks_*: optional injected dropout masks for the generator forward of each update."""
+        masks_*: optional injected dropout masks for the generator forward of each update.
+        estimator / eps_con: the estimator-conditioned trainer (t_est_train.py:214-283) — a frozen
+        module (B,3,H,W)->(B,nc) adds g_loss_w = MSE(estimator(fake), target) (:232,:237,
+        ops.py:37-39) and the reconstruction weight uses eps 1e-7 (:242); c_real is then
+        estimator(images).detach() (:219,:266-267), computed by the caller."""
         # --- D update (t_cls_train.py:288-312)
         self.d_opt.zero_grad()
         real = disc_forward(self.d, images, c_real, train)[0]
@@ -97,12 +102,19 @@ class Trainer:
         g_l1 = F.l1_loss(fake_img, images)                                # logged only (:255)
         diff = (fake_img - images).abs().mean(dim=(1, 2, 3))              # :259-262
         lmda = (c_real - c_target).abs().mean(dim=1)
-        loss_con = (diff / (lmda + 1e-2)).mean()
+        loss_con = (diff / (lmda + eps_con)).mean()
         g_loss = g_adv + loss_con
+        g_w = None
+        if estimator is not None:
+            g_w = F.mse_loss(estimator(fake_img), c_target)               # t_est_train.py:232,237
+            g_loss = g_loss + g_w
         g_loss.backward()
         self.g_opt.step()
-        return {"d_loss": d_loss.item(), "g_loss": g_loss.item(), "g_loss_adv": g_adv.item(),
-                "g_loss_l1": g_l1.item(), "loss_con": loss_con.item()}
+        out = {"d_loss": d_loss.item(), "g_loss": g_loss.item(), "g_loss_adv": g_adv.item(),
+               "g_loss_l1": g_l1.item(), "loss_con": loss_con.item()}
+        if g_w is not None:
+            out["g_loss_w"] = g_w.item()
+        return out
 
 
 def step_flops(H, W, B=1):
