@@ -45,36 +45,33 @@ __device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
 }
 
 // Philox4x32 (Salmon et al. 2011), 7 rounds (the smallest round count that passes BigCrush):
-// counter = 128-bit, key = 64-bit.
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+// counter = 128-bit, key = 64-bit.  The seven round keys (key + r * Weyl constant) are computed on
+// the host and arrive as a kernel parameter, so a round is two wide multiplies and two three-input
+// XORs whose key operand comes straight from the constant bank.
+struct PhiloxKeys {
+  uint32_t x[7], y[7];
+};
+static inline PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 7; ++r) {
+    k.x[r] = kx;
+    k.y[r] = ky;
+    kx += 0x9E3779B9u;
+    ky += 0xBB67AE85u;
+  }
+  return k;
+}
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, const PhiloxKeys& key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
   for (int r = 0; r < 7; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
+    const uint64_t p0 = (uint64_t)M0 * ctr.x, p1 = (uint64_t)M1 * ctr.z;
+    ctr = make_uint4((uint32_t)(p1 >> 32) ^ ctr.y ^ key.x[r], (uint32_t)p1,
+                     (uint32_t)(p0 >> 32) ^ ctr.w ^ key.y[r], (uint32_t)p0);
   }
   return ctr;
 }
-// Keep mask for the 8 channels of vector `vec_index`, laid out like packed bf16x2 data: 16 random
-// bits per element, lane = 0xFFFF iff u16 >= thr (one SIMD compare per element pair).
-__device__ __forceinline__ uint4 dropout_keepmask(uint64_t seed, uint64_t vec_index, uint32_t thr) {
-  const uint4 r = philox4x32(
-      make_uint4((uint32_t)vec_index, (uint32_t)(vec_index >> 32), 0x77755555u, 0u),
-      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const uint32_t t2 = thr | (thr << 16);
-  return make_uint4(__vcmpgeu2(r.x, t2), __vcmpgeu2(r.y, t2), __vcmpgeu2(r.z, t2),
-                    __vcmpgeu2(r.w, t2));
-}
-__host__ __device__ inline uint32_t dropout_threshold(float p) {
-  float t = p * 65536.f + 0.5f;
-  if (t < 0.f) t = 0.f;
-  if (t > 65535.f) t = 65535.f;
-  return (uint32_t)t;
-}
-
 // ------------------------------------------------------------------------------------------------
 // layout helpers
 // ------------------------------------------------------------------------------------------------
@@ -607,46 +604,126 @@ __device__ __forceinline__ uint4 byte_to_lanes(uint32_t b) {
   return make_uint4(byte_pair_to_lanes(b), byte_pair_to_lanes(b >> 2), byte_pair_to_lanes(b >> 4),
                     byte_pair_to_lanes(b >> 6));
 }
-template <int MODE>
-__device__ __forceinline__ uint4 keep_mask8(uint32_t thr, uint64_t seed,
-                                            const uint8_t* __restrict__ mask, long long vi) {
-  if (MODE == kDropNone) return make_uint4(~0u, ~0u, ~0u, ~0u);
-  if (MODE == kDropInjected) {
-    const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mask + vi * 8));
-    auto lanes = [](uint32_t two_bytes) -> uint32_t {
-      return ((two_bytes & 0xFFu) ? 0x0000FFFFu : 0u) | ((two_bytes & 0xFF00u) ? 0xFFFF0000u : 0u);
-    };
-    return make_uint4(lanes(mv.x), lanes(mv.x >> 16), lanes(mv.y), lanes(mv.y >> 16));
-  }
-  return dropout_keepmask(seed, (uint64_t)vi, thr);
+// injected uint8 keep mask (tests, golden fixtures): 8 bytes per vector -> bf16x2 lane masks
+__device__ __forceinline__ uint4 injected_keep8(const uint8_t* __restrict__ mask, long long vi) {
+  const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mask + vi * 8));
+  auto lanes = [](uint32_t two_bytes) -> uint32_t {
+    return ((two_bytes & 0xFFu) ? 0x0000FFFFu : 0u) | ((two_bytes & 0xFF00u) ? 0xFFFF0000u : 0u);
+  };
+  return make_uint4(lanes(mv.x), lanes(mv.x >> 16), lanes(mv.y), lanes(mv.y >> 16));
 }
 
-// grid = (ceil(2w * C/8 / 256), B * ceil(2h / kRowsPerThread)): a thread produces kRowsPerThread
-// consecutive output rows of its (column, 8-channel vector), so 16 independent 16-byte loads are in
-// flight per thread.  The kernel is instruction bound (RNG + interpolation per 16 output bytes), so
-// the dropout mode is a template parameter and all row-invariant index math is hoisted.  (8 rows per
-// thread: same time under ncu, 121 registers; 16 rows: 35 % slower.)
+// Philox keep decisions of one 8-channel vector for the forward kernel: 15 random bits per element
+// (rate resolution 2^-15), decided without a compare instruction: (u15 + 32768 - thr) carries into
+// bit 15 of its 16-bit lane iff u15 >= thr (no carry crosses the lane: the sum is < 65536), and one
+// PRMT replicates that bit over the lane (selector nibble 8 + k = "sign of byte k").
+__host__ __device__ inline uint32_t dropout_threshold15(float p) {
+  float t = p * 32768.f + 0.5f;
+  if (t < 0.f) t = 0.f;
+  if (t > 32767.f) t = 32767.f;
+  return (uint32_t)t;
+}
+// prmt.b32, generic mode: selector nibble n < 8 copies byte n of {a (0-3), b (4-7)}; n >= 8 fills the
+// byte with the sign bit of byte n - 8.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ void philox_keep8(const PhiloxKeys& keys, long long vi, uint32_t k2,
+                                             uint4& lanes, uint32_t& byte) {
+  const uint4 r = philox4x32(
+      make_uint4((uint32_t)vi, (uint32_t)((uint64_t)vi >> 32), 0x77755555u, 0u), keys);
+  const uint32_t s0 = (r.x & 0x7FFF7FFFu) + k2, s1 = (r.y & 0x7FFF7FFFu) + k2;
+  const uint32_t s2 = (r.z & 0x7FFF7FFFu) + k2, s3 = (r.w & 0x7FFF7FFFu) + k2;
+  lanes = make_uint4(prmt(s0, 0u, 0xBB99u), prmt(s1, 0u, 0xBB99u), prmt(s2, 0u, 0xBB99u),
+                     prmt(s3, 0u, 0xBB99u));
+  // bytes 1 and 3 of every word carry the decision in their top bit: gather the four decisions of two
+  // words as 0x00 / 0xFF bytes, keep one bit of each, and move them to bits 24..27 with one multiply
+  // (the partial products do not collide)
+  const uint32_t t0 = prmt(s0, s1, 0xFDB9u) & 0x01010101u;
+  const uint32_t t1 = prmt(s2, s3, 0xFDB9u) & 0x01010101u;
+  byte = ((t0 * 0x01020408u) >> 24) | (((t1 * 0x01020408u) >> 20) & 0xF0u);
+}
+
+// The blend is evaluated separably, on values that already carry the AdaIN affine map (the bilinear
+// weights sum to 1, so the map commutes with the blend; 1/(1-p) is folded into sc / sh):
+//   p' = sc * p + sh per source vector, H = p'_left + lx * (p'_right - p'_left) per source row and
+//   output column, o = H_top + ly * (H_bottom - H_top) per output vector.
+// Shared between the eight vectors of a thread's block this is 27 fp32 operations per output vector
+// instead of 49 for the four-weight form (the fma pipe, which also carries Philox's wide multiplies,
+// is the busiest pipe of this kernel).  Every step is an explicit fmaf / __fsub_rn so that the block
+// path and the general path round identically.
+__device__ __forceinline__ void affine8(const uint4& raw, const float (&sc)[8], const float (&sh)[8],
+                                        float (&o)[8]) {
+  float f[8];
+  unpack8(raw, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], sc[j], sh[j]);
+}
+__device__ __forceinline__ void lerp8(const float (&a)[8], const float (&diff)[8], float t,
+                                      float (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(t, diff[j], a[j]);
+}
+__device__ __forceinline__ void sub8(const float (&b)[8], const float (&a)[8], float (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = __fsub_rn(b[j], a[j]);
+}
+// One output vector from its two horizontally blended rows: vertical blend, dropout, store.
+template <int MODE>
+__device__ __forceinline__ void adain_emit(const float (&ht)[8], const float (&dv)[8], float ly,
+                                           long long vi, __nv_bfloat16* __restrict__ u,
+                                           uint8_t* __restrict__ keep_bits, uint32_t thr,
+                                           const PhiloxKeys& keys, const uint8_t* __restrict__ mask) {
+  float o[8];
+  lerp8(ht, dv, ly, o);
+  uint4 ov = pack8(o);
+  if (MODE == kDropPhilox) {
+    uint4 km;
+    uint32_t kb;
+    philox_keep8(keys, vi, thr, km, kb);
+    ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
+    keep_bits[vi] = (uint8_t)kb;
+  } else if (MODE == kDropInjected) {
+    const uint4 km = injected_keep8(mask, vi);
+    ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
+    keep_bits[vi] = (uint8_t)lanes_to_byte(km);
+  }
+  st_stream16(u + vi * 8, ov);
+}
+
+// grid = (ceil((w + 1) * C/8 / 256), B * (h/2 + 1)).  With align_corners=True and an exact x2 scale the
+// output columns 2k-1 and 2k blend the SAME source columns k-1 and k (src = dst (w-1)/(2w-1) lies in
+// [k-1, k) for both), and likewise for rows.  A thread therefore owns one 8-channel vector of a 4-row x
+// 2-column output block (rows 4j-1 .. 4j+2, columns 2k-1, 2k; k = 0 .. w) and produces its eight
+// output vectors from SIX source vectors (rows 2j-1, 2j, 2j+1 x columns k-1, k) that are loaded and
+// converted once: 0.75 loads and 6 conversions per output vector instead of 4 and 32 (the kernel is
+// instruction bound, not HBM bound).  Source indices and weights are still PyTorch's fp32 arithmetic
+// (bilinear_src); a thread whose computed indices differ from the block pattern (possible only where
+// src is an exact integer, i.e. the last row / column, through rounding) takes the general
+// four-loads-per-vector path, so the result never depends on the pattern being right.  An index may
+// differ where its weight is exactly zero (first row / column: PyTorch reads row 1 with weight 0).
 constexpr int kRowsPerThread = 4;
 template <int MODE>
 __global__ void __launch_bounds__(256)
 adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ u,
                          uint8_t* __restrict__ keep_bits, int h, int w, int C, float inv_keep,
-                         uint32_t thr, uint64_t seed, const uint8_t* __restrict__ mask, int xb_mul) {
+                         uint32_t thr, const __grid_constant__ PhiloxKeys keys,
+                         const uint8_t* __restrict__ mask, int xb_mul) {
   const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (xi >= Wo * cv) return;
-  const int X = xi / cv, v = xi - X * cv;
-  const int rows_per_img = (Ho + kRowsPerThread - 1) / kRowsPerThread;
-  const int b = blockIdx.y / rows_per_img;
-  const int Y0 = (blockIdx.y - b * rows_per_img) * kRowsPerThread;
+  if (xi >= (w + 1) * cv) return;
+  const int kx = xi / cv, v = xi - kx * cv;
+  const int groups = (h >> 1) + 1;  // row groups per image: rows 4j-1 .. 4j+2, j = 0 .. h/2
+  const int b = blockIdx.y / groups;
+  const int j4 = blockIdx.y - b * groups;
+  const int Y0 = 4 * j4 - 1;
   const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  int x0, x1;
-  float lx;
-  bilinear_src(X, rw, w, x0, x1, lx);
   const __nv_bfloat16* xb = x + (long long)(b * xb_mul) * h * w * C + v * 8;
-  const int o0 = x0 * C, o1 = x1 * C, row_pitch = w * C;  // 32-bit offsets inside one image
+  const int row_pitch = w * C;  // 32-bit offsets inside one image
   const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
   const float4* shp = reinterpret_cast<const float4*>(shift + (long long)b * C + v * 8);
   const float4 sc0 = __ldg(scp), sc1 = __ldg(scp + 1), sh0 = __ldg(shp), sh1 = __ldg(shp + 1);
@@ -654,45 +731,97 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
                        sc1.x * inv_keep, sc1.y * inv_keep, sc1.z * inv_keep, sc1.w * inv_keep};
   const float sh[8] = {sh0.x * inv_keep, sh0.y * inv_keep, sh0.z * inv_keep, sh0.w * inv_keep,
                        sh1.x * inv_keep, sh1.y * inv_keep, sh1.z * inv_keep, sh1.w * inv_keep};
-  uint4 ra[kRowsPerThread], rc[kRowsPerThread], rd[kRowsPerThread], re[kRowsPerThread];
-  float ly[kRowsPerThread];
+
+  // the block pattern: source columns cA, cB and source rows rr[0..2] (clamped to the image)
+  const int cA = max(kx - 1, 0), cB = min(kx, w - 1);
+  const int rr[3] = {max(2 * j4 - 1, 0), min(2 * j4, h - 1), min(2 * j4 + 1, h - 1)};
+  // PyTorch's indices and weights of the two columns and four rows, and whether they fit the pattern
+  const int X[2] = {2 * kx - 1, 2 * kx};
+  const bool okx[2] = {kx >= 1, kx < w};
+  int x0[2], x1[2];
+  float lx[2];
+  bool fast = true;
 #pragma unroll
-  for (int i = 0; i < kRowsPerThread; ++i) {
-    int y0, y1;
-    bilinear_src(min(Y0 + i, Ho - 1), rh, h, y0, y1, ly[i]);
-    const __nv_bfloat16* r0 = xb + y0 * row_pitch;
-    const __nv_bfloat16* r1 = xb + y1 * row_pitch;
-    ra[i] = ldg16(r0 + o0);
-    rc[i] = ldg16(r0 + o1);
-    rd[i] = ldg16(r1 + o0);
-    re[i] = ldg16(r1 + o1);
+  for (int q = 0; q < 2; ++q) {
+    bilinear_src(okx[q] ? X[q] : 0, rw, w, x0[q], x1[q], lx[q]);
+    if (okx[q]) fast = fast && x0[q] == cA && (x1[q] == cB || lx[q] == 0.f);
   }
-  long long vi = (((long long)b * Ho + Y0) * Wo + X) * cv + v;
+  int y0[4], y1[4];
+  float ly[4];
+  bool oky[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    oky[i] = (Y0 + i >= 0) && (Y0 + i < Ho);
+    bilinear_src(oky[i] ? Y0 + i : 0, rh, h, y0[i], y1[i], ly[i]);
+    if (oky[i]) fast = fast && y0[i] == rr[i >> 1] && (y1[i] == rr[(i >> 1) + 1] || ly[i] == 0.f);
+  }
   const long long vi_row = (long long)Wo * cv;
+  const long long vi00 = (((long long)b * Ho + Y0) * Wo + X[0]) * cv + v;  // (row Y0, column 2k-1)
+
+  if (fast) {
+    uint4 raw[3][2];
 #pragma unroll
-  for (int i = 0; i < kRowsPerThread; ++i, vi += vi_row) {
-    if (Y0 + i >= Ho) break;
-    float a[8], c[8], d[8], e[8];
-    unpack8(ra[i], a);
-    unpack8(rc[i], c);
-    unpack8(rd[i], d);
-    unpack8(re[i], e);
-    const uint4 km = keep_mask8<MODE>(thr, seed, mask, vi);
-    const float w00 = (1.f - ly[i]) * (1.f - lx), w01 = (1.f - ly[i]) * lx,
-                w10 = ly[i] * (1.f - lx), w11 = ly[i] * lx;
-    float o[8];
+    for (int r = 0; r < 3; ++r) {
+      raw[r][0] = ldg16(xb + rr[r] * row_pitch + cA * C);
+      raw[r][1] = ldg16(xb + rr[r] * row_pitch + cB * C);
+    }
+    // H[r][q]: source row r blended horizontally for output column q (affine map applied first)
+    float H[3][2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // bilinear weights sum to 1: interpolate x, then one fused affine map (1/(1-p) folded in)
-      const float xi2 = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
-      o[j] = fmaf(xi2, sc[j], sh[j]);
+    for (int r = 0; r < 3; ++r) {
+      float pl[8], pr[8], dx[8];
+      affine8(raw[r][0], sc, sh, pl);
+      affine8(raw[r][1], sc, sh, pr);
+      sub8(pr, pl, dx);
+      lerp8(pl, dx, lx[0], H[r][0]);
+      lerp8(pl, dx, lx[1], H[r][1]);
     }
-    uint4 ov = pack8(o);
-    if (MODE != kDropNone) {
-      ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
-      keep_bits[vi] = (uint8_t)lanes_to_byte(km);
+#pragma unroll
+    for (int pair = 0; pair < 2; ++pair) {  // rows 4j-1, 4j blend H[0], H[1]; rows 4j+1, 4j+2 H[1], H[2]
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!okx[q]) continue;
+        float dv[8];
+        sub8(H[pair + 1][q], H[pair][q], dv);
+#pragma unroll
+        for (int i = 2 * pair; i < 2 * pair + 2; ++i)
+          if (oky[i])
+            adain_emit<MODE>(H[pair][q], dv, ly[i], vi00 + i * vi_row + q * cv, u, keep_bits, thr, keys,
+                             mask);
+      }
     }
-    st_stream16(u + vi * 8, ov);
+    return;
+  }
+  // general path: four loads per output vector at PyTorch's own indices (recomputed here so that the
+  // index arrays above stay in registers)
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const int Y = Y0 + i;
+    if (Y < 0 || Y >= Ho) continue;
+    int ya, yb;
+    float lyy;
+    bilinear_src(Y, rh, h, ya, yb, lyy);
+    const __nv_bfloat16* r0 = xb + ya * row_pitch;
+    const __nv_bfloat16* r1 = xb + yb * row_pitch;
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {
+      const int XX = 2 * kx - 1 + q;
+      if (XX < 0 || XX >= Wo) continue;
+      int xa, xc;
+      float lxx;
+      bilinear_src(XX, rw, w, xa, xc, lxx);
+      float pl[8], pr[8], dx[8], ht[8], hb[8], dv[8];
+      affine8(ldg16(r0 + xa * C), sc, sh, pl);
+      affine8(ldg16(r0 + xc * C), sc, sh, pr);
+      sub8(pr, pl, dx);
+      lerp8(pl, dx, lxx, ht);
+      affine8(ldg16(r1 + xa * C), sc, sh, pl);
+      affine8(ldg16(r1 + xc * C), sc, sh, pr);
+      sub8(pr, pl, dx);
+      lerp8(pl, dx, lxx, hb);
+      sub8(hb, ht, dv);
+      adain_emit<MODE>(ht, dv, lyy, vi00 + i * vi_row + q * cv, u, keep_bits, thr, keys, mask);
+    }
   }
 }
 
@@ -1110,22 +1239,23 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
   WU_REQUIRE(p_drop == 0.f || keep_bits != nullptr,
              "wu_adain_up_drop_fwd: keep_bits is required when p_drop > 0");
-  const long long gy = (long long)B * ((2 * h + kRowsPerThread - 1) / kRowsPerThread);
-  WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_fwd: B*ceil(2h/4)=%lld exceeds 65535", gy);
-  dim3 grid((unsigned)((2 * w * (C / 8) + 255) / 256), (unsigned)gy);
+  const long long gy = (long long)B * (h / 2 + 1);
+  WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_fwd: B*(h/2+1)=%lld exceeds 65535", gy);
+  dim3 grid((unsigned)(((w + 1) * (C / 8) + 255) / 256), (unsigned)gy);
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_keep = 1.f / (1.f - p_drop);
   const int xm = x_bcast ? 0 : 1;
+  const PhiloxKeys keys = philox_keys(seed);
   if (p_drop == 0.f)
     adain_up_drop_fwd_kernel<kDropNone><<<grid, 256, 0, st>>>(
-        (const bf16*)x, scale, shift, (bf16*)u, nullptr, h, w, C, 1.f, 0u, seed, nullptr, xm);
+        (const bf16*)x, scale, shift, (bf16*)u, nullptr, h, w, C, 1.f, 0u, keys, nullptr, xm);
   else if (mask != nullptr)
     adain_up_drop_fwd_kernel<kDropInjected><<<grid, 256, 0, st>>>(
-        (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep, 1u, seed, mask, xm);
-  else
+        (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep, 1u, keys, mask, xm);
+  else  // thr argument = (32768 - thr15) in both 16-bit lanes (philox_keep8)
     adain_up_drop_fwd_kernel<kDropPhilox><<<grid, 256, 0, st>>>(
         (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep,
-        dropout_threshold(p_drop), seed, nullptr, xm);
+        (32768u - dropout_threshold15(p_drop)) * 0x00010001u, keys, nullptr, xm);
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
   return WU_OK;
 }
