@@ -321,7 +321,7 @@ def test_dropout_philox_rate(cuda):
     lw = torch.zeros(4 * C, nc, device=cuda)
     lb = torch.tensor([0.0, 2.0, 0.0, 2.0], device=cuda).repeat(C)  # y_mean 1, y_std > 0
     u0, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.0, 5, None)
-    u1, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.3, 5, None)
+    u1, st1 = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.3, 5, None)
     u2, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.3, 5, None)
     u3, _ = K.adain_up_drop(x, c, lw, lb, 1e-5, 0.3, 6, None)
     assert torch.equal(u1, u2) and not torch.equal(u1, u3)
@@ -331,6 +331,15 @@ def test_dropout_philox_rate(cuda):
     assert abs(rate - 0.7) < 0.01
     sel = kept & nz
     assert rel(u1[sel].float(), u0[sel].float() / 0.7) < 5e-3
+    # the keep byte the backward pass reads (bit j = channel 8v + j) is the decision the forward applied
+    bits = ((st1.bits.unsqueeze(-1).int() >> torch.arange(8, device=cuda)) & 1).bool().reshape(u1.shape)
+    assert torch.equal(bits[nz], kept[nz])
+    # and the backward honours it: dropped positions pass no gradient
+    gu = torch.ones_like(u1)
+    gx_keep, _, _ = K.adain_up_drop_bwd(gu, x, c, lw, lb, st1)
+    st1.bits.zero_()
+    gx_none, _, _ = K.adain_up_drop_bwd(gu, x, c, lw, lb, st1)
+    assert gx_none.float().abs().max().item() == 0.0 and gx_keep.float().abs().max().item() > 0.0
 
 
 def test_layout_roundtrip(cuda):
