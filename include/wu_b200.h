@@ -133,7 +133,9 @@ int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, cons
                        int C, int nc, int HW, float eps, int x_bcast, wu_stream_t stream);
 /* Step 3 (cunet.py:59-61): u[b,Y,X,c] = keep * bilinear_x2(x*scale+shift)[b,Y,X,c] / (1-p).
  * Dropout: p_drop == 0 -> none; else if mask != NULL it is a uint8 NHWC [B][2h][2w][C] keep mask;
- * else keep bits come from a Philox4x32-7 stream keyed by (seed, 8-channel vector index).
+ * else keep bits come from a Philox4x32-7 stream keyed by (seed, 8-channel vector index): 15 bits
+ * per element, keep iff u15 >= round(p * 32768), so the realised rate is 1-p to within 2^-16.
+ * Requires B * (h/2 + 1) <= 65535 (grid.y).
  * keep_bits (required when p_drop > 0): uint8 [B][2h][2w][C/8], bit j = channel 8v+j kept; the
  * backward pass reads it instead of replaying the RNG. */
 int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u,

@@ -634,8 +634,8 @@ __device__ __forceinline__ uint4 byte_to_lanes(uint32_t b) {
                     byte_pair_to_lanes(b >> 6));
 }
 // injected uint8 keep mask (tests, golden fixtures): 8 bytes per vector -> bf16x2 lane masks
-__device__ __forceinline__ uint4 injected_keep8(const uint8_t* __restrict__ mask, long long vi) {
-  const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mask + vi * 8));
+__device__ __forceinline__ uint4 injected_keep8(const uint8_t* __restrict__ mask, uint32_t vi) {
+  const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)vi * 8));
   auto lanes = [](uint32_t two_bytes) -> uint32_t {
     return ((two_bytes & 0xFFu) ? 0x0000FFFFu : 0u) | ((two_bytes & 0xFF00u) ? 0xFFFF0000u : 0u);
   };
@@ -652,10 +652,10 @@ __host__ __device__ inline uint32_t dropout_threshold15(float p) {
   if (t > 32767.f) t = 32767.f;
   return (uint32_t)t;
 }
-__device__ __forceinline__ void philox_keep8(const PhiloxKeys& keys, long long vi, uint32_t k2,
-                                             uint4& lanes, uint32_t& byte) {
-  const uint4 r = philox4x32(
-      make_uint4((uint32_t)vi, (uint32_t)((uint64_t)vi >> 32), 0x77755555u, 0u), keys);
+__device__ __forceinline__ void philox_keep8(const PhiloxKeys& keys, uint32_t vimg, uint32_t b,
+                                             uint32_t k2, uint4& lanes, uint32_t& byte) {
+  // counter = (8-channel vector index inside the image, image index, tag, 0)
+  const uint4 r = philox4x32(make_uint4(vimg, b, 0x77755555u, 0u), keys);
   const uint32_t s0 = (r.x & 0x7FFF7FFFu) + k2, s1 = (r.y & 0x7FFF7FFFu) + k2;
   const uint32_t s2 = (r.z & 0x7FFF7FFFu) + k2, s3 = (r.w & 0x7FFF7FFFu) + k2;
   lanes = make_uint4(prmt(s0, 0u, 0xBB99u), prmt(s1, 0u, 0xBB99u), prmt(s2, 0u, 0xBB99u),
@@ -692,10 +692,11 @@ __device__ __forceinline__ void sub8(const float (&b)[8], const float (&a)[8], f
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j] = __fsub_rn(b[j], a[j]);
 }
-// One output vector from its two horizontally blended rows: vertical blend, dropout, store.
+// One output vector from its two horizontally blended rows: vertical blend, dropout, store.  u, keep_bits
+// and mask point at image b; vimg is the vector index inside the image.
 template <int MODE>
 __device__ __forceinline__ void adain_emit(const float (&ht)[8], const float (&dv)[8], float ly,
-                                           long long vi, __nv_bfloat16* __restrict__ u,
+                                           uint32_t vimg, uint32_t b, __nv_bfloat16* __restrict__ u,
                                            uint8_t* __restrict__ keep_bits, uint32_t thr,
                                            const PhiloxKeys& keys, const uint8_t* __restrict__ mask) {
   float o[8];
@@ -704,18 +705,18 @@ __device__ __forceinline__ void adain_emit(const float (&ht)[8], const float (&d
   if (MODE == kDropPhilox) {
     uint4 km;
     uint32_t kb;
-    philox_keep8(keys, vi, thr, km, kb);
+    philox_keep8(keys, vimg, b, thr, km, kb);
     ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
-    keep_bits[vi] = (uint8_t)kb;
+    keep_bits[vimg] = (uint8_t)kb;
   } else if (MODE == kDropInjected) {
-    const uint4 km = injected_keep8(mask, vi);
+    const uint4 km = injected_keep8(mask, vimg);
     ov.x &= km.x; ov.y &= km.y; ov.z &= km.z; ov.w &= km.w;
-    keep_bits[vi] = (uint8_t)lanes_to_byte(km);
+    keep_bits[vimg] = (uint8_t)lanes_to_byte(km);
   }
-  st_stream16(u + vi * 8, ov);
+  st_stream16(u + (size_t)vimg * 8, ov);
 }
 
-// grid = (ceil((w + 1) * C/8 / 256), B * (h/2 + 1)).  With align_corners=True and an exact x2 scale the
+// grid = (ceil((w + 1) * C/8 / 256), h/2 + 1, B).  With align_corners=True and an exact x2 scale the
 // output columns 2k-1 and 2k blend the SAME source columns k-1 and k (src = dst (w-1)/(2w-1) lies in
 // [k-1, k) for both), and likewise for rows.  A thread therefore owns one 8-channel vector of a 4-row x
 // 2-column output block (rows 4j-1 .. 4j+2, columns 2k-1, 2k; k = 0 .. w) and produces its eight
@@ -734,17 +735,21 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ u,
                          uint8_t* __restrict__ keep_bits, int h, int w, int C, float inv_keep,
                          uint32_t thr, const __grid_constant__ PhiloxKeys keys,
-                         const uint8_t* __restrict__ mask, int xb_mul) {
+                         const uint8_t* __restrict__ mask, int xb_mul, float rh, float rw, int cv_shift) {
+  // rh = (h-1)/(2h-1), rw = (w-1)/(2w-1) in fp32 (PyTorch's ratio) and cv_shift = log2(C/8) or -1 come
+  // from the host: two fp32 divisions and an integer division per thread were a tenth of the kernel
   const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
   if (xi >= (w + 1) * cv) return;
-  const int kx = xi / cv, v = xi - kx * cv;
-  const int groups = (h >> 1) + 1;  // row groups per image: rows 4j-1 .. 4j+2, j = 0 .. h/2
-  const int b = blockIdx.y / groups;
-  const int j4 = blockIdx.y - b * groups;
+  const int kx = cv_shift >= 0 ? (xi >> cv_shift) : xi / cv;
+  const int v = xi - kx * cv;
+  const int b = blockIdx.z;
+  const int j4 = blockIdx.y;  // row group: rows 4j-1 .. 4j+2, j = 0 .. h/2
   const int Y0 = 4 * j4 - 1;
-  const float rh = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
-  const float rw = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const size_t img_vecs = (size_t)Ho * Wo * cv;
+  u += (size_t)b * img_vecs * 8;
+  if (MODE != kDropNone) keep_bits += (size_t)b * img_vecs;
+  if (MODE == kDropInjected) mask += (size_t)b * img_vecs * 8;
   const __nv_bfloat16* xb = x + (long long)(b * xb_mul) * h * w * C + v * 8;
   const int row_pitch = w * C;  // 32-bit offsets inside one image
   const float4* scp = reinterpret_cast<const float4*>(scale + (long long)b * C + v * 8);
@@ -778,8 +783,8 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
     bilinear_src(oky[i] ? Y0 + i : 0, rh, h, y0[i], y1[i], ly[i]);
     if (oky[i]) fast = fast && y0[i] == rr[i >> 1] && (y1[i] == rr[(i >> 1) + 1] || ly[i] == 0.f);
   }
-  const long long vi_row = (long long)Wo * cv;
-  const long long vi00 = (((long long)b * Ho + Y0) * Wo + X[0]) * cv + v;  // (row Y0, column 2k-1)
+  const int vi_row = Wo * cv;
+  const int vi00 = (Y0 * Wo + X[0]) * cv + v;  // (row Y0, column 2k-1); only valid (row, column) are used
 
   if (fast) {
     uint4 raw[3][2];
@@ -809,8 +814,8 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
 #pragma unroll
         for (int i = 2 * pair; i < 2 * pair + 2; ++i)
           if (oky[i])
-            adain_emit<MODE>(H[pair][q], dv, ly[i], vi00 + i * vi_row + q * cv, u, keep_bits, thr, keys,
-                             mask);
+            adain_emit<MODE>(H[pair][q], dv, ly[i], (uint32_t)(vi00 + i * vi_row + q * cv), (uint32_t)b, u,
+                             keep_bits, thr, keys, mask);
       }
     }
     return;
@@ -843,7 +848,8 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
       sub8(pr, pl, dx);
       lerp8(pl, dx, lxx, hb);
       sub8(hb, ht, dv);
-      adain_emit<MODE>(ht, dv, lyy, vi00 + i * vi_row + q * cv, u, keep_bits, thr, keys, mask);
+      adain_emit<MODE>(ht, dv, lyy, (uint32_t)(vi00 + i * vi_row + q * cv), (uint32_t)b, u, keep_bits, thr,
+                       keys, mask);
     }
   }
 }
@@ -1258,23 +1264,33 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
   WU_REQUIRE(p_drop == 0.f || keep_bits != nullptr,
              "wu_adain_up_drop_fwd: keep_bits is required when p_drop > 0");
-  const long long gy = (long long)B * (h / 2 + 1);
-  WU_REQUIRE(gy <= 65535, "wu_adain_up_drop_fwd: B*(h/2+1)=%lld exceeds 65535", gy);
-  dim3 grid((unsigned)(((w + 1) * (C / 8) + 255) / 256), (unsigned)gy);
+  WU_REQUIRE(B <= 65535 && h / 2 + 1 <= 65535, "wu_adain_up_drop_fwd: B=%d or h=%d exceeds the grid", B, h);
+  WU_REQUIRE((long long)4 * h * w * (C / 8) < (1ll << 31),
+             "wu_adain_up_drop_fwd: more than 2^31 vectors per image");
+  dim3 grid((unsigned)(((w + 1) * (C / 8) + 255) / 256), (unsigned)(h / 2 + 1), (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_keep = 1.f / (1.f - p_drop);
   const int xm = x_bcast ? 0 : 1;
   const PhiloxKeys keys = philox_keys(seed);
+  // PyTorch's fp32 ratio for align_corners=True (area_pixel_compute_scale): (in - 1) / (out - 1)
+  const float rh = 2 * h > 1 ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
+  const float rw = 2 * w > 1 ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
+  const int cv = C / 8;
+  int cv_shift = -1;
+  if ((cv & (cv - 1)) == 0)
+    for (cv_shift = 0; (1 << cv_shift) < cv; ++cv_shift) {}
   if (p_drop == 0.f)
     adain_up_drop_fwd_kernel<kDropNone><<<grid, 256, 0, st>>>(
-        (const bf16*)x, scale, shift, (bf16*)u, nullptr, h, w, C, 1.f, 0u, keys, nullptr, xm);
+        (const bf16*)x, scale, shift, (bf16*)u, nullptr, h, w, C, 1.f, 0u, keys, nullptr, xm, rh, rw,
+        cv_shift);
   else if (mask != nullptr)
     adain_up_drop_fwd_kernel<kDropInjected><<<grid, 256, 0, st>>>(
-        (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep, 1u, keys, mask, xm);
+        (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep, 1u, keys, mask, xm, rh, rw,
+        cv_shift);
   else  // thr argument = (32768 - thr15) in both 16-bit lanes (philox_keep8)
     adain_up_drop_fwd_kernel<kDropPhilox><<<grid, 256, 0, st>>>(
         (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep,
-        (32768u - dropout_threshold15(p_drop)) * 0x00010001u, keys, nullptr, xm);
+        (32768u - dropout_threshold15(p_drop)) * 0x00010001u, keys, nullptr, xm, rh, rw, cv_shift);
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
   return WU_OK;
 }
