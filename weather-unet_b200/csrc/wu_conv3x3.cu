@@ -364,29 +364,40 @@ struct ConvParams2 {
   __nv_bfloat16* pool_dst;
 };
 
-template <int BN, int T>
+// ABOX = 1 (WU_CONV_IMPL=3/4, not the default yet): ONE TMA box (64 ch, 10 px, 16T+2 rows) per channel
+// block serves all nine taps — tap (r, s) starts r * 1280 + s * 128 bytes into it and its 8-pixel row
+// groups are 1280 bytes apart.  The tensor core applies the 128-byte swizzle to the absolute
+// shared-memory address, so such starts read correctly (tools/scratch/umma_unaligned_probe.cu,
+// profiles/r01_umma_unaligned_start_probe.txt): 1.25x instead of 3x the tile's bytes cross L2 -> SM.
+// A stage is then recycled per channel block, not per column shift.
+template <int BN, int T, int ABOX = 0>
 struct ConvCfg2 {
   static constexpr int kARows = 16 * T + 2;
-  static constexpr int kABytes = kARows * 1024;
+  static constexpr int kRowPitch = ABOX ? 1280 : 1024;  // bytes per image row of an A stage
+  static constexpr int kATx = kARows * kRowPitch;       // bytes one TMA box delivers
+  static constexpr int kABytes = (kATx + 1023) / 1024 * 1024;  // stage stride (1024-byte aligned)
+  static constexpr int kSA = ABOX ? ((BN == 64 && T == 2) ? 3 : 2) : ((T == 4) ? 2 : 3);
+  static constexpr int kSB =
+      ABOX ? (BN == 64 ? (T == 4 ? 3 : 5) : 4) : (BN == 64 ? 5 : (BN == 128 ? 4 : 3));
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kSA = (T == 4) ? 2 : 3;
-  static constexpr int kSB = BN == 64 ? 5 : (BN == 128 ? 4 : 3);
-  static constexpr int kStagingBytes = 2 * 16384;
+  static constexpr int kNStg = (ABOX && BN == 64 && T == 4) ? 1 : 2;  // epilogue staging buffers
+  static constexpr int kStagingBytes = kNStg * 16384;
   static constexpr int kMaskBytes = 16384;  // dgrad: ReLU-mask tile of the next chunk (cp.async)
   static constexpr int kSmemBytes =
       kSA * kABytes + kSB * kBBytes + kStagingBytes + kMaskBytes + 1024 + 1024;
   static constexpr uint32_t kTmemCols = 2 * T * BN;
-  static_assert(kTmemCols == 512, "TMEM budget: 2 x T x BN must be 512 columns");
+  static_assert(kTmemCols == 512 || (ABOX && kTmemCols == 256),
+                "TMEM budget: 2 x T x BN must be 512 columns (256 for the ABOX T = 2 variant)");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int T, bool LAST, bool POOL>
+template <int BN, int T, bool LAST, bool POOL, int ABOX>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
                         const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmD, const ConvParams2 p) {
-  using Cfg = ConvCfg2<BN, T>;
+  using Cfg = ConvCfg2<BN, T, ABOX>;
   constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -465,14 +476,17 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
         decode(tile, b, h0, w0, n0);
         for (int cb = 0; cb < p.ctot_blocks; ++cb) {
           for (int s = 0; s < 3; ++s) {
-            mbar_wait(emptyA(sa), pa ^ 1u);
-            mbar_arrive_expect_tx(fullA(sa), Cfg::kABytes);
-            if (cb < p.c0_blocks)
-              tma_load_4d(a_base + sa * Cfg::kABytes, &tmA0, fullA(sa), cb * 64, w0 + s - 1, h0 - 1, b);
-            else
-              tma_load_4d(a_base + sa * Cfg::kABytes, &tmA1, fullA(sa), (cb - p.c0_blocks) * 64,
-                          w0 + s - 1, h0 - 1, b * p.b1_mul);
-            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            if (!ABOX || s == 0) {  // ABOX: one 10-pixel-wide box per channel block
+              const int wl = ABOX ? w0 - 1 : w0 + s - 1;
+              mbar_wait(emptyA(sa), pa ^ 1u);
+              mbar_arrive_expect_tx(fullA(sa), Cfg::kATx);
+              if (cb < p.c0_blocks)
+                tma_load_4d(a_base + sa * Cfg::kABytes, &tmA0, fullA(sa), cb * 64, wl, h0 - 1, b);
+              else
+                tma_load_4d(a_base + sa * Cfg::kABytes, &tmA1, fullA(sa), (cb - p.c0_blocks) * 64, wl,
+                            h0 - 1, b * p.b1_mul);
+              if (++sa == SA) { sa = 0; pa ^= 1u; }
+            }
             for (int r = 0; r < 3; ++r) {
               mbar_wait(emptyB(sb), pb ^ 1u);
               mbar_arrive_expect_tx(fullB(sb), Cfg::kBBytes);
@@ -490,7 +504,8 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       // descriptors are built once; per MMA only (byte offset >> 4) is added to the start-address
       // field (the single issuing thread's instruction count paces the tensor pipe at small N)
-      const uint64_t adesc0 = umma_smem_desc_sw128(a_base, 16, 1024);
+      constexpr int RP = Cfg::kRowPitch;  // bytes between the 8-pixel row groups of an A stage
+      const uint64_t adesc0 = umma_smem_desc_sw128(a_base, 16, RP);
       const uint64_t bdesc0 = umma_smem_desc_sw128(b_base, 16, 1024);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -502,20 +517,24 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
         const uint32_t d_tmem = tmem_base + buf * (T * BN);
         for (int cb = 0; cb < p.ctot_blocks; ++cb) {
           for (int s = 0; s < 3; ++s) {
-            mbar_wait(fullA(sa), pa);
-            tc_fence_after();
-            const uint64_t adesc_s = adesc0 + (uint64_t)((sa * Cfg::kABytes) >> 4);
+            if (!ABOX || s == 0) {
+              mbar_wait(fullA(sa), pa);
+              tc_fence_after();
+            }
+            // ABOX: the column shift is a 128-byte start offset into the one box of this channel block
+            const uint64_t adesc_s =
+                adesc0 + (uint64_t)((sa * Cfg::kABytes + (ABOX ? s * 128 : 0)) >> 4);
             for (int r = 0; r < 3; ++r) {
               mbar_wait(fullB(sb), pb);
               tc_fence_after();
               const uint64_t bdesc_s = bdesc0 + (uint64_t)((sb * Cfg::kBBytes) >> 4);
-              const uint64_t adesc_r = adesc_s + (uint64_t)((r * 1024) >> 4);
+              const uint64_t adesc_r = adesc_s + (uint64_t)((r * RP) >> 4);
               const uint32_t first = (cb | s | r) == 0 ? 1u : 0u;
 #pragma unroll
               for (int t = 0; t < T; ++t) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t adesc = adesc_r + (uint64_t)((16 * t * 1024 + k * 32) >> 4);
+                  const uint64_t adesc = adesc_r + (uint64_t)((16 * t * RP + k * 32) >> 4);
                   const uint64_t bdesc = bdesc_s + (uint64_t)((k * 32) >> 4);
                   umma_bf16(d_tmem + t * BN, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
                 }
@@ -523,8 +542,10 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
               umma_commit(emptyB(sb));
               if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
-            umma_commit(emptyA(sa));
-            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            if (!ABOX || s == 2) {
+              umma_commit(emptyA(sa));
+              if (++sa == SA) { sa = 0; pa ^= 1u; }
+            }
           }
         }
         umma_commit(tfull_bar(buf));
@@ -634,9 +655,9 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
               yo[2 * hw] = tanhf(a2);
             }
           }
-          const uint32_t sbuf = staging_base + (store_count & 1u) * 16384u;
+          const uint32_t sbuf = staging_base + (store_count % Cfg::kNStg) * 16384u;
           ++store_count;
-          if (issuer) tma_store_wait_read<1>();
+          if (issuer) tma_store_wait_read<Cfg::kNStg - 1>();
           named_bar_sync(1, 128);
           uint8_t* srow = smem + (sbuf - base) + row * 128;
 #pragma unroll
@@ -691,29 +712,35 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN, int T, bool LAST = false, bool POOL = false>
+template <int BN, int T, bool LAST = false, bool POOL = false, int ABOX = 0>
 static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
                         const CUtensorMap& dm, const ConvParams2& p, cudaStream_t st) {
-  using Cfg = ConvCfg2<BN, T>;
+  using Cfg = ConvCfg2<BN, T, ABOX>;
   static bool attr_done = false;
   if (!attr_done) {
-    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST, POOL>,
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST, POOL, ABOX>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv3x3_igemm_v2_kernel<BN, T, LAST, POOL><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
+  conv3x3_igemm_v2_kernel<BN, T, LAST, POOL, ABOX>
+      <<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_v2_kernel");
   return WU_OK;
 }
 
-// WU_CONV_IMPL: 0 / unset = per-shape choice, 1 = v1 everywhere, 2 = v2 everywhere (read once).
+// WU_CONV_IMPL: 0 / unset = per-shape choice, 1 = v1 everywhere, 2 = v2 everywhere (read once);
+// 3 / 4 = experimental one-box A loading for cout % 256 != 0 (ConvCfg2<.., ABOX = 1>; 3: T = 4 at
+// N = 64 with one staging buffer and three weight stages, 4: T = 2 at N = 64) — written at the end of
+// round 1 after the probe, NOT yet run on a GPU: validate with
+//   WU_CONV_IMPL=3 python -m pytest tests/test_kernels_gpu.py -m gpu -k "conv3x3_fprop or conv3x3_dgrad"
+//   WU_CONV_IMPL=3 python tools/layer_bench.py 64 256 10
 static int conv_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WU_CONV_IMPL");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 2) v = 0;
+    if (v < 0 || v > 4) v = 0;
   }
   return v;
 }
@@ -1452,8 +1479,10 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
   WU_REQUIRE(cout > 0 && cout % 64 == 0 && cout != 192 && (cout <= 256 || cout % 256 == 0),
              "wu_conv3x3_fprop: cout=%d must be 64, 128 or a multiple of 256", cout);
   const int bn = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
-  if (conv_impl() == 2 || (conv_impl() == 0 && bn < 256)) {
-    const int T = bn == 64 ? 4 : (bn == 128 ? 2 : 1);
+  const int abox = (conv_impl() >= 3 && bn < 256) ? conv_impl() : 0;
+  if (conv_impl() == 2 || abox || (conv_impl() == 0 && bn < 256)) {
+    const int T = bn == 64 ? (abox == 4 ? 2 : 4) : (bn == 128 ? 2 : 1);
+    const int bw = abox ? 10 : 8;  // pixels per row of an A box
     ConvParams2 q;
     q.c0_blocks = c0 / 64;
     q.ctot_blocks = (c0 + c1) / 64;
@@ -1476,9 +1505,9 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     q.pool_dst = nullptr;
     CUtensorMap a0, a1, bm, dm;
     int rc;
-    if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, 8, 16 * T + 2)) != WU_OK) return rc;
+    if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, bw, 16 * T + 2)) != WU_OK) return rc;
     if (c1 > 0) {
-      if ((rc = make_act_tmap(&a1, src1, src1_bcast ? 1 : B, H, W, c1, c1, 8, 16 * T + 2)) != WU_OK)
+      if ((rc = make_act_tmap(&a1, src1, src1_bcast ? 1 : B, H, W, c1, c1, bw, 16 * T + 2)) != WU_OK)
         return rc;
     } else {
       a1 = a0;
@@ -1486,6 +1515,11 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * (c0 + c1), bn)) != WU_OK) return rc;
     if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, 8, 16)) != WU_OK) return rc;
     cudaStream_t st2 = (cudaStream_t)stream;
+    if (abox) {
+      if (bn == 128) return launch_conv2<128, 2, false, false, 1>(a0, a1, bm, dm, q, st2);
+      return abox == 4 ? launch_conv2<64, 2, false, false, 1>(a0, a1, bm, dm, q, st2)
+                       : launch_conv2<64, 4, false, false, 1>(a0, a1, bm, dm, q, st2);
+    }
     switch (bn) {
       case 64: return launch_conv2<64, 4>(a0, a1, bm, dm, q, st2);
       case 128: return launch_conv2<128, 2>(a0, a1, bm, dm, q, st2);
