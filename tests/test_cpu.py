@@ -195,3 +195,72 @@ def test_spectral_norm_record_layout():
     members = re.findall(r"^\s*(?:const )?\w+\* \w+;", body, flags=re.M)
     assert len(members) == 14 and "int rows, cols;" in body, members
     assert "(120 bytes)" in open(os.path.join(ROOT, "include", "wu_b200.h")).read()
+
+
+def _prmt(a, b, sel):
+    """prmt.b32 in generic mode (PTX ISA): nibble n < 8 copies byte n of {a, b}; n >= 8 replicates
+    the sign bit of byte n - 8."""
+    by = [(a >> (8 * i)) & 0xFF for i in range(4)] + [(b >> (8 * i)) & 0xFF for i in range(4)]
+    out = 0
+    for i in range(4):
+        n = (sel >> (4 * i)) & 0xF
+        v = by[n & 7]
+        if n & 8:
+            v = 0xFF if v & 0x80 else 0
+        out |= v << (8 * i)
+    return out
+
+
+def test_dropout_keep_bit_arithmetic():
+    """The compare-free keep decision of adain_up_drop_fwd (csrc/wu_elementwise.cu::philox_keep8),
+    restated with the constants read from the source: for every threshold and random word the bf16x2
+    lane masks and the keep byte equal the plain definition keep = (u15 >= thr15)."""
+    src = open(os.path.join(ROOT, "weather-unet_b200", "csrc", "wu_elementwise.cu")).read()
+    body = src[src.index("void philox_keep8("):]
+    body = body[:body.index("\n}\n")]
+    mask15 = int(re.search(r"r\.x & (0x[0-9A-Fa-f]+)u\) \+ k2", body).group(1), 16)
+    sel_lanes = int(re.search(r"prmt\(s0, 0u, (0x[0-9A-Fa-f]+)u\)", body).group(1), 16)
+    sel_gather = int(re.search(r"prmt\(s0, s1, (0x[0-9A-Fa-f]+)u\)", body).group(1), 16)
+    bitmask = int(re.search(r"& (0x0[0-9A-Fa-f]+)u;\n  const uint32_t t1", body).group(1), 16)
+    mult = int(re.search(r"t0 \* (0x[0-9A-Fa-f]+)u", body).group(1), 16)
+    assert mask15 == 0x7FFF7FFF
+    launch = src[src.index('extern "C" int wu_adain_up_drop_fwd('):]
+    assert "(32768u - dropout_threshold15(p_drop)) * 0x00010001u" in launch
+    rng = np.random.default_rng(0)
+    M = 0xFFFFFFFF
+    for thr in [0, 1, 9830, 16384, 32766, 32767] + [int(t) for t in rng.integers(0, 32768, 20)]:
+        k2 = ((32768 - thr) * 0x00010001) & M
+        for _ in range(200):
+            r = [int(v) for v in rng.integers(0, 1 << 32, 4, dtype=np.uint64)]
+            s = [((x & mask15) + k2) & M for x in r]
+            lanes = [_prmt(x, 0, sel_lanes) for x in s]
+            t0 = _prmt(s[0], s[1], sel_gather) & bitmask
+            t1 = _prmt(s[2], s[3], sel_gather) & bitmask
+            byte = (((t0 * mult) & M) >> 24) | ((((t1 * mult) & M) >> 20) & 0xF0)
+            for k in range(4):
+                lo, hi = (r[k] & 0x7FFF) >= thr, ((r[k] >> 16) & 0x7FFF) >= thr
+                assert lanes[k] == (0xFFFF if lo else 0) | (0xFFFF0000 if hi else 0)
+                assert (byte >> (2 * k)) & 1 == int(lo) and (byte >> (2 * k + 1)) & 1 == int(hi)
+    # threshold rounding: p = 0.3 -> 9830 / 32768 (rate error 1.2e-5), p = 0 keeps everything
+    assert int(0.3 * 32768 + 0.5) == 9830
+
+
+def test_upsample_block_pattern():
+    """The index pattern adain_up_drop_fwd's block path relies on: with align_corners=True
+    and an exact x2 scale, output columns 2k-1 and 2k take source columns k-1 and k under PyTorch's
+    fp32 index arithmetic, except where the source coordinate is an exact integer (first / last
+    column), where the kernel's general path or a zero weight covers it."""
+    for w in (4, 5, 7, 8, 16, 32, 64, 128, 256):
+        ratio = np.float32(w - 1) / np.float32(2 * w - 1)
+        for k in range(0, w + 1):
+            for X in (2 * k - 1, 2 * k):
+                if X < 0 or X >= 2 * w:
+                    continue
+                sx = np.float32(ratio * np.float32(X))
+                x0 = min(int(sx), w - 1)
+                x1 = x0 + (1 if x0 < w - 1 else 0)
+                lam = float(sx - np.float32(x0))
+                cA, cB = max(k - 1, 0), min(k, w - 1)
+                fits = x0 == cA and (x1 == cB or lam == 0.0)
+                interior = 0 < X < 2 * w - 1
+                assert fits or not interior, (w, k, X, x0, x1, lam)
