@@ -98,6 +98,81 @@ probe(const __grid_constant__ CUtensorMap tmX, float* out, int mode, int row_pit
   if (warp == 0) tmem_dealloc<64>(tmem);
 }
 
+// Second question (weight-gradient kernels, both operands MN-major: the contiguous 128 bytes are the
+// 64 channels of one pixel, GEMM-K is the pixel): D[m][n] = sum_px A[px][m] * B[px][n] with
+// A = [tap (r, s) | tap (r, s + 1)] (two 64-channel atoms ONE pixel = 128 bytes apart: LBO = 128),
+// 8-pixel K groups one image row = 1280 bytes apart (SBO = 1280), start = base + r * 1280 + s * 128,
+// and B = the 64 x 64 identity over (pixel, column).  Then D[m][n] = X[r + n / 8][s + (m >= 64) + n % 8][m % 64].
+__global__ void __launch_bounds__(128, 1)
+probe_mn(const __grid_constant__ CUtensorMap tmX, float* out, int row_pitch_bytes) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const uint32_t raw = smem_u32(sm);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* s = sm + (base - raw);
+  const uint32_t a_base = base, b_base = base + kAAlloc;
+  const uint32_t full = b_base + 8192, done = full + 8, slot = full + 16;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(slot);
+  // B[k = pixel][n]: row k at k * 128 (8-pixel groups 1 KiB apart), chunk (n / 8) ^ (k & 7); identity
+  if (tid < 64) {
+    for (int ck = 0; ck < 8; ++ck) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ck == (tid >> 3)) {
+        uint16_t e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e[tid & 7] = 0x3F80;
+        v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+      }
+      *reinterpret_cast<uint4*>(s + kAAlloc + tid * 128 + ((ck ^ (tid & 7)) << 4)) = v;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(s + kAAlloc + 8192 + 16);
+  if (tid == 0) {
+    mbar_arrive_expect_tx(full, kABytes);
+    tma_load_4d(a_base, &tmX, full, 0, 0, 0, 0);
+    mbar_wait(full, 0);
+  }
+  __syncthreads();
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // both MN-major
+  for (int cs = 0; cs < 6; ++cs) {  // r = 0..2, s = 0..1 (the second atom is column s + 1 <= 2)
+    const int r = cs / 2, sft = cs % 2;
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t start = a_base + r * row_pitch_bytes + sft * 128;
+      const uint64_t adesc = umma_smem_desc_sw128(start, 128, row_pitch_bytes);
+      const uint64_t bdesc = umma_smem_desc_sw128(b_base, 8192, 1024);
+      for (int k = 0; k < 4; ++k)  // K = 16 pixels = two image rows
+        umma_bf16(tmem, adesc + (uint64_t)((k * 2 * row_pitch_bytes) >> 4),
+                  bdesc + (uint64_t)((k * 2048) >> 4), idesc, k > 0 ? 1u : 0u);
+      umma_commit(done);
+      mbar_wait(done, cs & 1);
+    }
+    __syncthreads();
+    tc_fence_after();
+    uint32_t v0[32], v1[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    tmem_ld_32x32(taddr, v0);
+    tmem_ld_32x32(taddr + 32, v1);
+    tmem_ld_wait();
+    float* o = out + ((size_t)cs * 128 + tid) * 64;
+    for (int j = 0; j < 32; ++j) {
+      o[j] = __uint_as_float(v0[j]);
+      o[32 + j] = __uint_as_float(v1[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
 static float xval(int row, int px, int ch) {
   // (row, px) in the mantissa (1..180 < 256: exact in bf16), the 16-byte chunk in the exponent, the
   // parity of the channel in the sign
@@ -156,7 +231,38 @@ int main() {
       printf("\n");
     }
   }
-  printf(all_ok ? "RESULT: unaligned starts with a 1280-byte row pitch read correctly in both modes\n"
-                : "RESULT: see mismatches above\n");
+  printf(all_ok ? "RESULT (K-major): unaligned starts with a 1280-byte row pitch read correctly in both modes\n"
+                : "RESULT (K-major): see mismatches above\n");
+  // ---- MN-major operands (weight gradient)
+  cudaFuncSetAttribute(probe_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaMemset(dout, 0xFF, 9 * 128 * 64 * 4);
+  probe_mn<<<1, 128, smem>>>(tm, dout, kPx * 128);
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("MN-major, A = [tap (r,s) | tap (r,s+1)] (LBO 128, SBO 1280): run %s\n", cudaGetErrorString(e));
+  if (e != cudaSuccess) return 1;
+  std::vector<float> o(6 * 128 * 64);
+  cudaMemcpy(o.data(), dout, o.size() * 4, cudaMemcpyDeviceToHost);
+  int mn_ok = 1;
+  for (int cs = 0; cs < 6; ++cs) {
+    const int r = cs / 2, s = cs % 2;
+    int bad = 0, fm = -1, fn = -1;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 64; ++n) {
+        const float want = xval(r + n / 8, s + (m >= 64 ? 1 : 0) + n % 8, m % 64);
+        if (o[((size_t)cs * 128 + m) * 64 + n] != want) {
+          if (fm < 0) { fm = m; fn = n; }
+          ++bad;
+        }
+      }
+    printf("  tap r=%d s=%d|%d: %s (%d of 8192 wrong)", r, s, s + 1, bad ? "MISMATCH" : "ok", bad);
+    if (bad) {
+      mn_ok = 0;
+      printf("  first wrong D[%d][%d] = %g, want %g", fm, fn, o[((size_t)cs * 128 + fm) * 64 + fn],
+             xval(r + fn / 8, s + (fm >= 64 ? 1 : 0) + fn % 8, fm % 64));
+    }
+    printf("\n");
+  }
+  printf(mn_ok ? "RESULT (MN-major): one 10-pixel box serves neighbouring column shifts of the weight gradient\n"
+               : "RESULT (MN-major): see mismatches above\n");
   return 0;
 }
