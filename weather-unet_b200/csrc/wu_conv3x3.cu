@@ -733,8 +733,8 @@ static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
 // 3 / 4 = experimental one-box A loading for cout % 256 != 0 (ConvCfg2<.., ABOX = 1>; 3: T = 4 at
 // N = 64 with one staging buffer and three weight stages, 4: T = 2 at N = 64) — written at the end of
 // round 1 after the probe, NOT yet run on a GPU: validate with
-//   WU_CONV_IMPL=3 python -m pytest tests/test_kernels_gpu.py -m gpu -k "conv3x3_fprop or conv3x3_dgrad"
-//   WU_CONV_IMPL=3 python tools/layer_bench.py 64 256 10
+//   tools/check_conv_impl.sh   (parity tests, per-layer timings and one bench step under each setting;
+//   3 also covers the fused last / pool layers, 4 leaves those on the default kernel)
 static int conv_impl() {
   static int v = -1;
   if (v < 0) {
@@ -1571,6 +1571,7 @@ extern "C" int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_pac
   WU_REQUIRE(B > 0 && H > 0 && W > 0, "wu_conv3x3_fprop_last: bad shape B=%d H=%d W=%d", B, H, W);
   WU_REQUIRE(cin > 0 && cin % 64 == 0, "wu_conv3x3_fprop_last: cin=%d must be a positive multiple of 64", cin);
   constexpr int T = 4;
+  const bool abox = conv_impl() == 3;  // experimental one-box A loading (see conv_impl())
   ConvParams2 q;
   q.c0_blocks = q.ctot_blocks = cin / 64;
   q.tiles_w = (W + 7) / 8;
@@ -1593,9 +1594,10 @@ extern "C" int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_pac
   q.pool_dst = nullptr;
   CUtensorMap a0, bm, dm;
   int rc;
-  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
+  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, abox ? 10 : 8, 16 * T + 2)) != WU_OK) return rc;
   if ((rc = make_mat_tmap(&bm, w_packed, 64, 9 * cin, 64)) != WU_OK) return rc;
   if ((rc = make_act_tmap(&dm, dst, B, H, W, 64, 64, 8, 16)) != WU_OK) return rc;
+  if (abox) return launch_conv2<64, T, true, false, 1>(a0, a0, bm, dm, q, (cudaStream_t)stream);
   return launch_conv2<64, T, true>(a0, a0, bm, dm, q, (cudaStream_t)stream);
 }
 
@@ -1608,6 +1610,7 @@ extern "C" int wu_conv3x3_fprop_pool(const void* src, int cin, const void* w_pac
   WU_REQUIRE(cin > 0 && cin % 64 == 0, "wu_conv3x3_fprop_pool: cin=%d must be a positive multiple of 64", cin);
   WU_REQUIRE(cout == 64 || cout == 128, "wu_conv3x3_fprop_pool: cout=%d must be 64 or 128", cout);
   const int T = cout == 64 ? 4 : 2;
+  const bool abox = conv_impl() == 3;  // experimental one-box A loading (see conv_impl())
   ConvParams2 q;
   q.c0_blocks = q.ctot_blocks = cin / 64;
   q.tiles_w = (W + 7) / 8;
@@ -1629,10 +1632,13 @@ extern "C" int wu_conv3x3_fprop_pool(const void* src, int cin, const void* w_pac
   q.pool_dst = (__nv_bfloat16*)pool_dst;
   CUtensorMap a0, bm, dm;
   int rc;
-  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
+  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, abox ? 10 : 8, 16 * T + 2)) != WU_OK) return rc;
   if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * cin, cout)) != WU_OK) return rc;
   if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, 8, 16)) != WU_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (abox)
+    return cout == 64 ? launch_conv2<64, 4, false, true, 1>(a0, a0, bm, dm, q, st)
+                      : launch_conv2<128, 2, false, true, 1>(a0, a0, bm, dm, q, st);
   return cout == 64 ? launch_conv2<64, 4, false, true>(a0, a0, bm, dm, q, st)
                     : launch_conv2<128, 2, false, true>(a0, a0, bm, dm, q, st);
 }
