@@ -250,14 +250,29 @@ int wu_sn_forward(const void* tensors, int n_tensors, const void* wtu_chunks, in
 int wu_sn_backward(const void* tensors, const void* dot_chunks, int n_dot_chunks,
                    const void* bwd_chunks, int n_bwd_chunks, wu_stream_t stream);
 
-/* ---- multi-tensor Adam (t_cls_train.py:184-185) ---------------------------------
+/* ---- multi-tensor Adam that also emits the packed bf16 weights (t_cls_train.py:184-185,273,311;
+ * SURVEY §8 f2 / k15) --------------------------------------------------------------------------
  * torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, no amsgrad)
- * for a whole parameter list in one launch.  `tensors`: device array of records
- * {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64 numel} (40 bytes);
- * `chunks`: device array of {int32 tensor; int32 count; int64 start} (16 bytes), one CTA each.
- * `step` is the 1-based step count of this update. */
+ * for a whole parameter list in one launch.  `tensors`: device array of 64-byte records
+ *   {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64 numel;
+ *    bf16* w_fprop; bf16* w_dgrad; int32 cout; int32 cin}
+ * w_fprop == NULL: ordinary tensor.  Otherwise `param` is a 3x3 convolution weight [cout][cin][3][3]
+ * (cout %% 16 == 0, cin %% 64 == 0) and the launch rewrites its operand layouts (see
+ * wu_pack_conv3x3_weights; w_dgrad may be NULL) from the updated master, so the next
+ * forward(x, c) (t_cls_train.py:302,242) runs on the weights g_opt.step() (:273) just produced
+ * without a separate pack pass.
+ * `chunks`: device array of {int32 tensor; int32 count; int64 start} (16 bytes), one CTA each; for a
+ * packed tensor count = 0 and start = tile index over (cout/16) x (cin/64) tiles (row-major, see
+ * wu_adam_pack_tile).
+ * `step` is the 1-based step count of this update when step_state == NULL.  With step_state (device,
+ * 16 bytes: {int32 step; float bc1; float rsqrt_bc2; int32 pad}, zero-initialised by the caller) the
+ * count lives on the device and is advanced by the call itself: the update can then be replayed
+ * from a CUDA graph. */
 int wu_adam_multi(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, int step, wu_stream_t stream);
+                  float beta2, float eps, float weight_decay, int step, void* step_state,
+                  wu_stream_t stream);
+/* Tile of a packed weight one chunk covers: *co output channels x *ci input channels (x 9 taps). */
+int wu_adam_pack_tile(int* co, int* ci);
 
 /* ---- per-sample L1 distance (t_cls_train.py:255,259-266; ops.py:22-24) ------------
  * d[s] = mean_i |a[s][i] - b[s][i]| over the n elements of sample s (fp32, contiguous), one pass; the

@@ -264,3 +264,28 @@ def test_upsample_block_pattern():
                 fits = x0 == cA and (x1 == cB or lam == 0.0)
                 interior = 0 < X < 2 * w - 1
                 assert fits or not interior, (w, k, X, x0, x1, lam)
+
+
+def test_adam_tables_layout():
+    """Host side of wu_adam_multi (optim.build_tables): 64-byte tensor records in the field order the
+    header documents, one 16-byte chunk per 8192 elements of an ordinary tensor and one per
+    16 x 64 x 9 tile of a packed 3x3 weight; tile constants agree with the CUDA source."""
+    import re
+    import struct
+    from weather_unet_b200 import optim
+    src = open(os.path.join(ROOT, "weather-unet_b200", "csrc", "wu_optim.cu")).read()
+    m = re.search(r"kPackCo = (\d+), kPackCi = (\d+)", src)
+    assert (int(m.group(1)), int(m.group(2))) == (optim.PACK_CO, optim.PACK_CI)
+    items = [dict(p=0x1000, g=0x2000, m=0x3000, v=0x4000, n=20000),
+             dict(p=0x5000, g=0x6000, m=0x7000, v=0x8000, n=128 * 192 * 9, wf=0x9000, wd=0xA000,
+                  cout=128, cin=192)]
+    trec, crec, n = optim.build_tables(items)
+    assert len(trec) == 2 * 64 and len(crec) == 16 * n
+    assert n == 3 + (128 // 16) * (192 // 64)
+    r1 = struct.unpack_from("<QQQQqQQii", trec, 64)
+    assert r1 == (0x5000, 0x6000, 0x7000, 0x8000, 128 * 192 * 9, 0x9000, 0xA000, 128, 192)
+    chunks = [struct.unpack_from("<iiq", crec, 16 * i) for i in range(n)]
+    assert chunks[:3] == [(0, 8192, 0), (0, 8192, 8192), (0, 20000 - 16384, 16384)]
+    assert chunks[3:] == [(1, 0, t) for t in range(24)]
+    with pytest.raises(ValueError):
+        optim.build_tables([dict(p=1, g=2, m=3, v=4, n=9 * 8 * 64, wf=5, wd=6, cout=8, cin=64)])

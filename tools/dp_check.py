@@ -37,7 +37,7 @@ sl = slice(rank * per, (rank + 1) * per)
 
 G, D = build()
 step = GDTrainStep(G, D, lr=0.0)
-assert step.distributed and G._grad_sink is not None
+assert step.distributed and step._use_sink
 step.step(x[sl], cr[sl], ct[sl], masks_d=tuple(m[sl] for m in md), masks_g=tuple(m[sl] for m in mg))
 torch.cuda.synchronize()
 dp = {("G." + n): p.grad.detach().clone() for n, p in G.named_parameters() if p.grad is not None}

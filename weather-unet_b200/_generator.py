@@ -29,25 +29,59 @@ def param_names():
 PARAM_NAMES = param_names()
 
 
+PACKED_NAMES = tuple(f"{b}.{i}.weight" for b in BLOCKS for i in (0, 2) if (b, i) != ("dconv_down1", 0))
+
+
 class PackedWeights:
-    """bf16 K-major copies of the 13 tensor-core convolution weights, refreshed when the fp32
-    master parameter changes (tracked through the tensor version counter)."""
+    """bf16 K-major copies (w_fprop, w_dgrad) of the 13 tensor-core convolution weights.
+
+    One persistent pair of buffers per weight (stable addresses: the optimiser's device tables and
+    captured CUDA graphs point at them).  A copy is valid for one (storage, version) of its fp32
+    master: any in-place change of the master bumps its version counter and the next `get` repacks,
+    unless the writer has already rewritten the copies itself and said so (`mark_fresh`: the fused
+    Adam launch does, optim.py)."""
 
     def __init__(self):
-        self._cache = {}
+        self._buf = {}   # name -> (wf, wd)
+        self._key = {}   # name -> (data_ptr, version, device) the copies were made from
+
+    @staticmethod
+    def _key_of(w):
+        return (w.data_ptr(), w._version, w.device)
+
+    def buffers(self, name, w):
+        """The (w_fprop, w_dgrad) buffers of `name`, allocated for `w`'s shape / device if needed
+        (contents unspecified until `get` or a writer fills them)."""
+        hit = self._buf.get(name)
+        cout, cin = w.shape[0], w.shape[1]
+        if hit is None or hit[0].device != w.device or hit[0].shape != (cout, 9 * cin):
+            hit = (torch.empty((cout, 9 * cin), dtype=torch.bfloat16, device=w.device),
+                   torch.empty((cin, 9 * cout), dtype=torch.bfloat16, device=w.device))
+            self._buf[name] = hit
+            self._key.pop(name, None)
+        return hit
 
     def get(self, name, w):
-        key = (w.data_ptr(), w._version, w.device)
-        hit = self._cache.get(name)
-        if hit is not None and hit[0] == key:
-            return hit[1], hit[2]
-        with torch.no_grad():
-            wf, wd = K.pack_conv3x3_weights(w.detach())
-        self._cache[name] = (key, wf, wd)
+        wf, wd = self.buffers(name, w)
+        key = self._key_of(w)
+        if self._key.get(name) != key:
+            with torch.no_grad():
+                K.pack_conv3x3_weights_into(w.detach(), wf, wd)
+            self._key[name] = key
         return wf, wd
 
+    def mark_fresh(self, name, w):
+        """The caller has just rewritten the copies of `name` from the current contents of `w`."""
+        if name in self._buf:
+            self._key[name] = self._key_of(w)
+
+    def invalidate(self):
+        """Forget which masters the copies were made from (buffers and their addresses stay)."""
+        self._key.clear()
+
     def clear(self):
-        self._cache.clear()
+        self._buf.clear()
+        self._key.clear()
 
 
 class _CUNetFn(torch.autograd.Function):
@@ -93,22 +127,31 @@ class _CUNetFn(torch.autograd.Function):
         up1b, y = K.conv3x3_last(up1a, wf("dconv_up1.2.weight"), P["dconv_up1.2.bias"],
                                  P["conv_last.weight"], P["conv_last.bias"])
 
-        ctx.acts = dict(x=x, c=c, a1=a1, conv1=conv1, p1=p1, d2a=d2a, conv2=conv2, p2=p2, d3a=d3a,
+        # x, c, the output and the parameters go through save_for_backward so that autograd notices
+        # an in-place change between forward and backward (e.g. an optimiser step in between)
+        ctx.save_for_backward(x, c, y, *params)
+        ctx.acts = dict(a1=a1, conv1=conv1, p1=p1, d2a=d2a, conv2=conv2, p2=p2, d3a=d3a,
                         conv3=conv3, p3=p3, d4a=d4a, x4=x4, u3=u3, up3a=up3a, up3b=up3b, u2=u2,
-                        up2a=up2a, up2b=up2b, u1=u1, up1a=up1a, up1b=up1b, y=y)
+                        up2a=up2a, up2b=up2b, u1=u1, up1a=up1a, up1b=up1b)
         ctx.sts = (st3, st2, st1)
-        ctx.params = P
         ctx.packed = packed
         ctx.grad_sink = opts.get("grad_sink")
         if opts.get("keep_acts") is not None:
-            opts["keep_acts"].update(ctx.acts)
+            opts["keep_acts"].update(ctx.acts, x=x, c=c, y=y)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        A, P, packed = ctx.acts, ctx.params, ctx.packed
+        # the autograd engine's thread may have another current device: launch where the data is
+        with torch.cuda.device(gy.device):
+            return _CUNetFn._backward(ctx, gy)
+
+    @staticmethod
+    def _backward(ctx, gy):
+        x, c, y, *params = ctx.saved_tensors
+        P = dict(zip(PARAM_NAMES, params))
+        A, packed = dict(ctx.acts, x=x, c=c, y=y), ctx.packed
         st3, st2, st1 = ctx.sts
-        c = A["c"]
         sink = ctx.grad_sink
 
         class _Grads(dict):
@@ -268,11 +311,16 @@ def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=Non
     if seed is None:
         # host RNG draw (no device sync); three sites use seed, seed+1, seed+2
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
-    if one_to_many and keep_acts is None:
-        return transfer_forward(module, x, c, masks, seed)
     params = [module.get_parameter(n) for n in PARAM_NAMES]
-    opts = dict(training=training, p=module.dropout.p, masks=masks, seed=seed,
-                eps=(module.adain3.eps, module.adain2.eps, module.adain1.eps),
-                packed=module._packed, keep_acts=keep_acts,
-                grad_sink=getattr(module, "_grad_sink", None))
-    return _CUNetFn.apply(x, c, opts, *params)
+    if any(p.device != x.device for p in params):
+        raise RuntimeError("Conditional_UNet: input and parameters are on different devices")
+    # kernels, TMA descriptors and the stream all belong to the device that holds the tensors, which
+    # need not be the caller's current device
+    with torch.cuda.device(x.device):
+        if one_to_many and keep_acts is None:
+            return transfer_forward(module, x, c, masks, seed)
+        opts = dict(training=training, p=module.dropout.p, masks=masks, seed=seed,
+                    eps=(module.adain3.eps, module.adain2.eps, module.adain1.eps),
+                    packed=module._packed, keep_acts=keep_acts,
+                    grad_sink=getattr(module, "_grad_sink", None))
+        return _CUNetFn.apply(x, c, opts, *params)

@@ -65,7 +65,8 @@ SIGNATURES = {
     "wu_sn_wv_rows": (I, []),
     "wu_sn_forward": (I, [P, I, P, I, P, I, P, I, I, F, P]),
     "wu_sn_backward": (I, [P, P, I, P, I, P]),
-    "wu_adam_multi": (I, [P, P, I, F, F, F, F, F, I, P]),
+    "wu_adam_multi": (I, [P, P, I, F, F, F, F, F, I, P, P]),
+    "wu_adam_pack_tile": (I, [P, P]),
     "wu_l1_per_sample_workspace_bytes": (SZ, [I]),
     "wu_l1_per_sample_fwd": (I, [P, P, P, I, c_longlong, P, SZ, P]),
     "wu_l1_per_sample_bwd": (I, [P, P, P, P, I, c_longlong, P]),

@@ -25,6 +25,11 @@ def pack_conv3x3_weights(w, need_dgrad=True):
     return wf, wd
 
 
+def pack_conv3x3_weights_into(w, wf, wd):
+    """Same, into caller-held buffers (wd may be None)."""
+    call("wu_pack_conv3x3_weights", ptr(w), w.shape[0], w.shape[1], ptr(wf), ptr(wd), stream())
+
+
 def conv3x3(src0, src1, w_packed, bias, relu, mask, cout, src1_bcast=False):
     """3x3/s1/p1 convolution over the (virtual) channel concat [src0, src1]; see wu_conv3x3_fprop.
     src1_bcast: src1 has batch 1 and is shared by every image of src0."""

@@ -8,14 +8,14 @@ import torch.nn as nn
 try:  # package import (weather_unet_b200.cunet)
     from .utils import AdaIN, HalfDropout, BatchNorm  # noqa: F401
     from .nets import r_double_conv
-    from ._generator import generator_forward, PackedWeights
+    from ._generator import generator_forward, PackedWeights, PACKED_NAMES
 except ImportError:  # flat import with this directory on sys.path (`from cunet import ...`)
     import os as _os
     import sys as _sys
     _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
     from weather_unet_b200.utils import AdaIN, HalfDropout, BatchNorm  # noqa: F401
     from weather_unet_b200.nets import r_double_conv
-    from weather_unet_b200._generator import generator_forward, PackedWeights
+    from weather_unet_b200._generator import generator_forward, PackedWeights, PACKED_NAMES
 
 
 class Conditional_UNet(nn.Module):
@@ -69,6 +69,16 @@ class Conditional_UNet(nn.Module):
         ``seed`` = explicit dropout seed.  Dropout follows ``self.training`` like nn.Dropout."""
         return generator_forward(self, x, c, dropout_masks=dropout_masks, seed=seed,
                                  keep_acts=_keep_acts)
+
+    def packed_weight_names(self):
+        """Names of the parameters that have derived bf16 operand copies in `self._packed` (what
+        optim.FusedAdam.attach_packed maintains)."""
+        return PACKED_NAMES
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._packed.invalidate()  # copy_() bumps the version counters anyway; belt and braces
+        return out
 
     def _apply(self, fn, *args, **kwargs):
         self._packed.clear()  # .cuda()/.to() move the master weights: drop derived copies

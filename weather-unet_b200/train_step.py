@@ -96,8 +96,8 @@ class GradBuckets:
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-                flat.div_(self.world)
+                # NCCL averages inside the collective: no separate scaling kernel per bucket
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
         else:  # CPU / gloo (tests)
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             flat.div_(self.world)
@@ -143,18 +143,24 @@ class GDTrainStep:
             distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.distributed = bool(distributed)
         self.g_buckets = self.d_buckets = None
+        self._use_sink = False
         if self.distributed:
             skip = tuple(n for n, _ in G.named_parameters() if n.endswith("emb.weight"))
             self.g_buckets = GradBuckets(G.named_parameters(), group, skip=skip)
             self.d_buckets = GradBuckets(D.named_parameters(), group)
             self.d_buckets.attach_autograd_hooks()
-            if overlap and hasattr(G, "_grad_sink"):
-                G._grad_sink = self.g_buckets  # the generator's backward writes into the buckets
-            else:
+            # the generator's backward writes its gradients straight into the buckets; the sink is
+            # handed to the module only around the G update's forward (step()), so a backward
+            # outside the trainer never touches the buckets
+            self._use_sink = bool(overlap and hasattr(G, "_grad_sink"))
+            if not self._use_sink:
                 self.g_buckets.attach_autograd_hooks()
             for m in (G, D):  # identical replicas to start from
-                for t in list(m.parameters()) + list(m.buffers()):
-                    dist.broadcast(t.data, src=0, group=group)
+                with torch.no_grad():
+                    for t in list(m.parameters()) + list(m.buffers()):
+                        # detach() shares the version counter (unlike .data): caches keyed on it
+                        # (the generator's packed bf16 weights) see the overwrite
+                        dist.broadcast(t.detach(), src=0, group=group)
         # t_cls_train.py:184-185: Adam, betas (0, 0.999), L2 weight decay lr/20 (not AdamW)
         if fused_adam is None:
             fused_adam = next(G.parameters()).is_cuda
@@ -164,6 +170,10 @@ class GDTrainStep:
             Adam = torch.optim.Adam
         self.g_opt = Adam(G.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
         self.d_opt = Adam(D.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
+        if fused_adam and hasattr(G, "packed_weight_names"):
+            # g_opt.step() (t_cls_train.py:273) must reach the bf16 operand copies the tensor-core
+            # convolutions read: the same launch rewrites them
+            self.g_opt.attach_packed(G)
 
     def _disc(self, x, c):
         if self.d_channels_last and not (self.d_autocast and x.dtype == torch.float32):
@@ -172,6 +182,16 @@ class GDTrainStep:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return self.D(x, c)[0].float()
         return self.D(x, c)[0]
+
+    def _g_forward(self, images, c, masks):
+        """The generator forward whose backward feeds the G update."""
+        if not self._use_sink:
+            return self.G(images, c, dropout_masks=masks)
+        self.G._grad_sink = self.g_buckets
+        try:
+            return self.G(images, c, dropout_masks=masks)
+        finally:
+            self.G._grad_sink = None
 
     def _zero(self, opt, buckets):
         if buckets is not None:
@@ -187,7 +207,7 @@ class GDTrainStep:
         self._zero(self.d_opt, self.d_buckets)
         real = self._disc(images, c_real)
         if self.share_fake:
-            shared = G(images, c_target, dropout_masks=masks_g)  # one forward for both updates
+            shared = self._g_forward(images, c_target, masks_g)  # one forward for both updates
             fake_img = shared.detach()
         else:
             with torch.no_grad():  # the reference builds this graph and drops it with .detach() (:302-303)
@@ -201,7 +221,7 @@ class GDTrainStep:
         # discriminator's gradient all-reduce is awaited and its Adam step applied: in data-parallel
         # runs the reduction (one bucket that completes at the very end of D's backward) hides under
         # the generator's convolutions.  Same arithmetic, same order of updates as the reference.
-        fake_img = shared if self.share_fake else G(images, c_target, dropout_masks=masks_g)
+        fake_img = shared if self.share_fake else self._g_forward(images, c_target, masks_g)
         if self.d_buckets is not None:
             self.d_buckets.finish()
         self.d_opt.step()
