@@ -55,7 +55,11 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  device_step=False):
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        # torch.optim.Adam's group keys (so that state_dict()s are interchangeable both ways); the
+        # options this implementation does not have are pinned to torch's defaults
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False,
+                        maximize=False, foreach=None, capturable=False, differentiable=False,
+                        fused=None, decoupled_weight_decay=False)
         super().__init__(params, defaults)
         self._packed = None       # _generator.PackedWeights whose copies this optimiser maintains
         self._packed_of = {}      # id(param) -> name in that cache
@@ -141,6 +145,8 @@ class FusedAdam(torch.optim.Optimizer):
                 st["step"] += 1
                 steps.add(int(st["step"]))
             b1, b2 = group["betas"]
+            if group.get("amsgrad") or group.get("maximize") or group.get("decoupled_weight_decay"):
+                raise RuntimeError("FusedAdam: amsgrad / maximize / decoupled weight decay are not implemented")
             with torch.cuda.device(dev):
                 if len(steps) > 1:
                     # parameters that joined late carry their own bias correction (torch semantics):
