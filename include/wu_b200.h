@@ -141,6 +141,15 @@ int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, cons
 int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u,
                          uint8_t* keep_bits, int B, int h, int w, int C, float p_drop, uint64_t seed,
                          const uint8_t* mask, int x_bcast, wu_stream_t stream);
+/* Same with a device-resident draw counter: `epoch` (device uint32, may be NULL = 0) is read by the
+ * kernel and its low 16 bits enter the Philox counter next to the image index, so the same launch
+ * replayed from a CUDA graph draws a fresh mask once the caller has advanced *epoch (nn.Dropout draws
+ * a new mask per forward: cunet.py:61,68,75).  epoch == NULL or *epoch == 0 reproduces
+ * wu_adain_up_drop_fwd bit for bit. */
+int wu_adain_up_drop_fwd_epoch(const void* x, const float* scale, const float* shift, void* u,
+                               uint8_t* keep_bits, int B, int h, int w, int C, float p_drop,
+                               uint64_t seed, const uint32_t* epoch, const uint8_t* mask, int x_bcast,
+                               wu_stream_t stream);
 /* AdaIN without the fused upsample / dropout (utils.py:49-50 on its own): out = x*scale + shift,
  * scale / shift from wu_adain_style_fwd.  x, out NHWC bf16 [B][HW][C]. */
 int wu_adain_apply(const void* x, const float* scale, const float* shift, void* out, int B, int HW,

@@ -238,3 +238,58 @@ def test_train50_parameter_trajectory(cuda):
                 and stale["med_conv"] > band_ac["med_conv"] - 0.1
                 and stale["tail_err"] < max(0.15, 1.5 * band_ac["tail_err"])), \
         "the criteria cannot see frozen weights"
+
+
+def test_graphed_step_matches_eager(cuda):
+    """GraphedGDStep replays exactly the iteration GDTrainStep.step runs eagerly: same losses and
+    bit-identical parameters after several iterations on changing batches, a fresh dropout mask per
+    replay (device-side draw counter), Adam's bias correction advancing on the device."""
+    from weather_unet_b200.train_step import GDTrainStep, GraphedGDStep
+    g = torch.Generator().manual_seed(21)
+    batches = []
+    for _ in range(4):
+        x = (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).to(cuda)
+        cr = torch.eye(5)[torch.randint(0, 5, (2,), generator=g)].to(cuda)
+        ct = torch.eye(5)[torch.randint(0, 5, (2,), generator=g)].to(cuda)
+        batches.append((x, cr, ct))
+
+    def make():
+        G, D = _mk(cuda)
+        G.use_device_dropout_counter(True)
+        G._drop_seed = 12345
+        return G, D, GDTrainStep(G, D, lr=1e-3, static_grads=True)
+
+    Ga, Da, ta = make()
+    Gb, Db, tb = make()
+    eager, graphed = [], []
+    for i in range(2):  # GraphedGDStep runs 2 eager warm-up iterations on the first batch
+        eager.append({k: float(v) for k, v in ta.step(*batches[0]).items()})
+    gs = GraphedGDStep(tb, *batches[0], warmup=2)
+    assert gs.library_launches > 100
+    for i in range(6):
+        eager.append({k: float(v) for k, v in ta.step(*batches[i % 4]).items()})
+        graphed.append({k: float(v) for k, v in gs.step(*batches[i % 4]).items()})
+    for e, r in zip(eager[2:], graphed):
+        assert e == r, (e, r)
+    # a new mask per replay: the same batch twice in a row gives different losses
+    l1 = float(gs.step(*batches[0])["g_loss_l1"])
+    ta.step(*batches[0])
+    l2 = float(gs.step(*batches[0])["g_loss_l1"])
+    ta.step(*batches[0])
+    assert l1 != l2
+    for (n, p), (_, q) in zip(list(Ga.named_parameters()) + list(Da.named_parameters()),
+                              list(Gb.named_parameters()) + list(Db.named_parameters())):
+        assert torch.equal(p, q), n
+    for (n, p), (_, q) in zip(Da.named_buffers(), Db.named_buffers()):
+        assert torch.equal(p, q), n
+    # the host mirrors of Adam's step count followed the replays
+    sa = {int(s["step"]) for s in ta.g_opt.state.values()}
+    sb = {int(s["step"]) for s in tb.g_opt.state.values()}
+    assert sa == sb == {10}
+    # and the operand copies the graph maintains are the packed masters
+    from weather_unet_b200 import _ops as K
+    for n in Gb.packed_weight_names():
+        w = Gb.get_parameter(n).detach()
+        wf, wd = Gb._packed.buffers(n, w)
+        rf, rd = K.pack_conv3x3_weights(w)
+        assert torch.equal(wf, rf) and torch.equal(wd, rd), n

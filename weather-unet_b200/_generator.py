@@ -93,6 +93,7 @@ class _CUNetFn(torch.autograd.Function):
         p_drop = opts["p"] if opts["training"] else 0.0
         masks = opts.get("masks") or (None, None, None)
         seed = opts.get("seed", 0)
+        epoch = opts.get("epoch")
         eps = opts["eps"]
 
         def wf(name):
@@ -115,13 +116,13 @@ class _CUNetFn(torch.autograd.Function):
         d4a, x4 = block(p3, None, "dconv_down4")
         # decoder (cunet.py:59-78)
         u3, st3 = K.adain_up_drop(x4, c, P["adain3.l1.weight"], P["adain3.l1.bias"], eps[0], p_drop,
-                                  seed, masks[0])
+                                  seed, masks[0], epoch=epoch)
         up3a, up3b = block(u3, conv3, "dconv_up3")
         u2, st2 = K.adain_up_drop(up3b, c, P["adain2.l1.weight"], P["adain2.l1.bias"], eps[1], p_drop,
-                                  seed + 1, masks[1])
+                                  seed + 1, masks[1], epoch=epoch)
         up2a, up2b = block(u2, conv2, "dconv_up2")
         u1, st1 = K.adain_up_drop(up2b, c, P["adain1.l1.weight"], P["adain1.l1.bias"], eps[2], p_drop,
-                                  seed + 2, masks[2])
+                                  seed + 2, masks[2], epoch=epoch)
         # last block: its second convolution also applies conv_last + tanh from registers (cunet.py:78-82)
         up1a = K.conv3x3(u1, conv1, wf("dconv_up1.0.weight"), P["dconv_up1.0.bias"], True, None, 64)
         up1b, y = K.conv3x3_last(up1a, wf("dconv_up1.2.weight"), P["dconv_up1.2.bias"],
@@ -161,12 +162,23 @@ class _CUNetFn(torch.autograd.Function):
 
             def __setitem__(self, name, t):
                 if sink is not None and t is not None and name in sink.where:
-                    sink.grad_view(name).copy_(t.view_as(P[name]))
+                    v = sink.grad_view(name)
+                    if t.data_ptr() != v.data_ptr():  # not produced in place (see `dst`)
+                        v.copy_(t.view_as(P[name]))
                     sink.ready(name)
                     t = None
                 dict.__setitem__(self, name, t)
 
         G = _Grads()
+
+        def dst(name):
+            """Where the kernel should write the gradient of `name`: its slot in the all-reduce
+            bucket when there is one (no copy kernel afterwards), else a fresh tensor (None)."""
+            if sink is not None and name in sink.where:
+                v = sink.grad_view(name)
+                if v.is_contiguous():
+                    return v
+            return None
 
         def wd(name):
             return packed.get(name, P[name])[1]
@@ -176,18 +188,22 @@ class _CUNetFn(torch.autograd.Function):
             Returns the gradient at `src`, masked by relu'(mask_src) when given."""
             cin = P[f"{name}.0.weight"].shape[1]
             cout = P[f"{name}.0.weight"].shape[0]
-            G[f"{name}.2.weight"], G[f"{name}.2.bias"] = K.conv3x3_wgrad(a, None, g_b)
+            G[f"{name}.2.weight"], G[f"{name}.2.bias"] = K.conv3x3_wgrad(
+                a, None, g_b, dw=dst(f"{name}.2.weight"), db=dst(f"{name}.2.bias"))
             g_a = K.conv3x3(g_b, None, wd(f"{name}.2.weight"), None, False, a, cout)
-            G[f"{name}.0.weight"], G[f"{name}.0.bias"] = K.conv3x3_wgrad(src, None, g_a)
+            G[f"{name}.0.weight"], G[f"{name}.0.bias"] = K.conv3x3_wgrad(
+                src, None, g_a, dw=dst(f"{name}.0.weight"), db=dst(f"{name}.0.bias"))
             return K.conv3x3(g_a, None, wd(f"{name}.0.weight"), None, False, mask_src, cin)
 
         def up_block_bwd(name, u, skip, a, g_b):
             """Backward of a decoder r_double_conv fed by the virtual concat [u, skip]."""
             c0, c1 = u.shape[3], skip.shape[3]
             cout = a.shape[3]
-            G[f"{name}.2.weight"], G[f"{name}.2.bias"] = K.conv3x3_wgrad(a, None, g_b)
+            G[f"{name}.2.weight"], G[f"{name}.2.bias"] = K.conv3x3_wgrad(
+                a, None, g_b, dw=dst(f"{name}.2.weight"), db=dst(f"{name}.2.bias"))
             g_a = K.conv3x3(g_b, None, wd(f"{name}.2.weight"), None, False, a, cout)
-            G[f"{name}.0.weight"], G[f"{name}.0.bias"] = K.conv3x3_wgrad(u, skip, g_a)
+            G[f"{name}.0.weight"], G[f"{name}.0.bias"] = K.conv3x3_wgrad(
+                u, skip, g_a, dw=dst(f"{name}.0.weight"), db=dst(f"{name}.0.bias"))
             w_d = wd(f"{name}.0.weight")  # [c0 + c1][9 * cout]: row slices are the two sources
             g_u = K.conv3x3(g_a, None, w_d[:c0], None, False, None, c0)
             g_skip = K.conv3x3(g_a, None, w_d[c0:], None, False, None, c1)
@@ -195,13 +211,15 @@ class _CUNetFn(torch.autograd.Function):
 
         def adain_bwd(name, g_u, x_in, st):
             gx, dlw, dlb = K.adain_up_drop_bwd(g_u, x_in, c, P[f"{name}.l1.weight"],
-                                               P[f"{name}.l1.bias"], st)
+                                               P[f"{name}.l1.bias"], st, dlw=dst(f"{name}.l1.weight"),
+                                               dlb=dst(f"{name}.l1.bias"))
             G[f"{name}.l1.weight"], G[f"{name}.l1.bias"] = dlw, dlb
             return gx
 
         gy = gy.contiguous().float()
         g_up1b, G["conv_last.weight"], G["conv_last.bias"] = K.conv_last_tanh_bprop(
-            gy, A["y"], A["up1b"], P["conv_last.weight"])
+            gy, A["y"], A["up1b"], P["conv_last.weight"], dw=dst("conv_last.weight"),
+            db=dst("conv_last.bias"))
         g_u1, g_skip1 = up_block_bwd("dconv_up1", A["u1"], A["conv1"], A["up1a"], g_up1b)
         g_up2b = adain_bwd("adain1", g_u1, A["up2b"], st1)
         g_u2, g_skip2 = up_block_bwd("dconv_up2", A["u2"], A["conv2"], A["up2a"], g_up2b)
@@ -216,9 +234,11 @@ class _CUNetFn(torch.autograd.Function):
         g_p1 = plain_block_bwd("dconv_down2", A["p1"], A["d2a"], g_conv2, None)
         g_conv1 = K.maxpool2_bwd(A["conv1"], g_p1, g_skip1)
 
-        G["dconv_down1.2.weight"], G["dconv_down1.2.bias"] = K.conv3x3_wgrad(A["a1"], None, g_conv1)
+        G["dconv_down1.2.weight"], G["dconv_down1.2.bias"] = K.conv3x3_wgrad(
+            A["a1"], None, g_conv1, dw=dst("dconv_down1.2.weight"), db=dst("dconv_down1.2.bias"))
         g_a1 = K.conv3x3(g_conv1, None, wd("dconv_down1.2.weight"), None, False, A["a1"], 64)
-        G["dconv_down1.0.weight"], G["dconv_down1.0.bias"] = K.conv_first_wgrad(A["x"], g_a1)
+        G["dconv_down1.0.weight"], G["dconv_down1.0.bias"] = K.conv_first_wgrad(
+            A["x"], g_a1, dw=dst("dconv_down1.0.weight"), db=dst("dconv_down1.0.bias"))
 
         ctx.acts = None
         grads = []
@@ -230,7 +250,7 @@ class _CUNetFn(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
-def transfer_forward(module, x1, c, masks, seed):
+def transfer_forward(module, x1, c, masks, seed, epoch=None):
     """One image x many conditions (inference/inf_1year_signals.py:98-107: every batch row is the
     same image, dataset.py:200-203): the encoder (cunet.py:45-54, 26.8 of 84.8 GFLOP) and the AdaIN
     statistics of the bottleneck run ONCE on the single image; the decoder runs per condition and
@@ -257,13 +277,13 @@ def transfer_forward(module, x1, c, masks, seed):
     conv3 = block(p2, None, "dconv_down3")
     x4 = block(K.maxpool2(conv3), None, "dconv_down4")
     u3, _ = K.adain_up_drop(x4, c, P["adain3.l1.weight"], P["adain3.l1.bias"], module.adain3.eps,
-                            p_drop, seed, masks[0], x_bcast=True)
+                            p_drop, seed, masks[0], x_bcast=True, epoch=epoch)
     h = block(u3, conv3, "dconv_up3", bcast=True)
     u2, _ = K.adain_up_drop(h, c, P["adain2.l1.weight"], P["adain2.l1.bias"], module.adain2.eps,
-                            p_drop, seed + 1, masks[1])
+                            p_drop, seed + 1, masks[1], epoch=epoch)
     h = block(u2, conv2, "dconv_up2", bcast=True)
     u1, _ = K.adain_up_drop(h, c, P["adain1.l1.weight"], P["adain1.l1.bias"], module.adain1.eps,
-                            p_drop, seed + 2, masks[2])
+                            p_drop, seed + 2, masks[2], epoch=epoch)
     a = K.conv3x3(u1, conv1, wf("dconv_up1.0.weight"), P["dconv_up1.0.bias"], True, None, 64,
                   src1_bcast=True)
     return K.conv3x3_last(a, wf("dconv_up1.2.weight"), P["dconv_up1.2.bias"], P["conv_last.weight"],
@@ -308,7 +328,13 @@ def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=Non
         for m, s in zip(masks, want):
             if tuple(m.shape) != s or m.dtype != torch.uint8:
                 raise ValueError(f"dropout mask must be uint8 NHWC {s}, got {m.dtype} {tuple(m.shape)}")
-    if seed is None:
+    epoch = None
+    if seed is None and training and masks is None and getattr(module, "_drop_epoch", None) is not None:
+        # device-side draw counter (Conditional_UNet.use_device_dropout_counter): one base seed, the
+        # counter advances on the device with every forward — what a CUDA-graph replay needs
+        seed, epoch = module._drop_seed, module._drop_epoch
+        epoch.add_(1)
+    elif seed is None:
         # host RNG draw (no device sync); three sites use seed, seed+1, seed+2
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
     params = [module.get_parameter(n) for n in PARAM_NAMES]
@@ -318,8 +344,8 @@ def generator_forward(module, x, c, dropout_masks=None, seed=None, keep_acts=Non
     # need not be the caller's current device
     with torch.cuda.device(x.device):
         if one_to_many and keep_acts is None:
-            return transfer_forward(module, x, c, masks, seed)
-        opts = dict(training=training, p=module.dropout.p, masks=masks, seed=seed,
+            return transfer_forward(module, x, c, masks, seed, epoch)
+        opts = dict(training=training, p=module.dropout.p, masks=masks, seed=seed, epoch=epoch,
                     eps=(module.adain3.eps, module.adain2.eps, module.adain1.eps),
                     packed=module._packed, keep_acts=keep_acts,
                     grad_sink=getattr(module, "_grad_sink", None))

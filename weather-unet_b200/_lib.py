@@ -39,6 +39,7 @@ SIGNATURES = {
     "wu_adain_stats_chunks": (I, [I]),
     "wu_adain_stats": (I, [P, P, I, I, I, P]),
     "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
+    "wu_adain_up_drop_fwd_epoch": (I, [P, P, P, P, P, I, I, I, I, F, U64, P, P, I, P]),
     "wu_adain_apply": (I, [P, P, P, P, I, I, I, P]),
     "wu_adain_up_drop_fwd": (I, [P, P, P, P, P, I, I, I, I, F, U64, P, I, P]),
     "wu_adain_bwd_chunks": (I, [I, I, I]),

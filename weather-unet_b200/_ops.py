@@ -63,16 +63,19 @@ def conv3x3_pool(src, w_packed, bias, cout):
     return dst, pooled
 
 
-def conv3x3_wgrad(src0, src1, dy, want_bias=True):
-    """-> (dw fp32 [cout][cin][3][3], db fp32 [cout] or None)."""
+def conv3x3_wgrad(src0, src1, dy, want_bias=True, dw=None, db=None):
+    """-> (dw fp32 [cout][cin][3][3], db fp32 [cout] or None).  dw / db: optional caller-held
+    destinations (e.g. views into a flat gradient bucket)."""
     B, H, W, c0 = src0.shape
     c1 = 0 if src1 is None else src1.shape[3]
     cout = dy.shape[3]
     cin = c0 + c1
     nbytes = query("wu_conv3x3_wgrad_workspace_bytes", cin, cout, B, H, W)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dy.device)
-    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dy.device)
-    db = torch.empty((cout,), dtype=torch.float32, device=dy.device) if want_bias else None
+    if dw is None:
+        dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dy.device)
+    if want_bias and db is None:
+        db = torch.empty((cout,), dtype=torch.float32, device=dy.device)
     call("wu_conv3x3_wgrad", ptr(src0), c0, ptr(src1), c1, ptr(dy), cout, B, H, W, ptr(dw), ptr(db),
          ptr(ws), nbytes, stream())
     return dw, db
@@ -86,12 +89,14 @@ def conv_first(x, w, bias):
     return dst
 
 
-def conv_first_wgrad(x, dy):
+def conv_first_wgrad(x, dy, dw=None, db=None):
     B, _, H, W = x.shape
     nbytes = query("wu_conv_first_wgrad_workspace_bytes", B, H, W)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
-    dw = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=x.device)
-    db = torch.empty((64,), dtype=torch.float32, device=x.device)
+    if dw is None:
+        dw = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=x.device)
+    if db is None:
+        db = torch.empty((64,), dtype=torch.float32, device=x.device)
     call("wu_conv_first_wgrad", ptr(x), ptr(dy), ptr(dw), ptr(db), B, H, W, ptr(ws), nbytes, stream())
     return dw, db
 
@@ -104,13 +109,15 @@ def conv_last_tanh(x, w, bias):
     return y
 
 
-def conv_last_tanh_bprop(gy, y, x, w):
+def conv_last_tanh_bprop(gy, y, x, w, dw=None, db=None):
     B, H, W, _ = x.shape
     nbytes = query("wu_conv_last_tanh_bprop_workspace_bytes", B, H, W)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
     gx = torch.empty_like(x)
-    dw = torch.empty((3, 64, 1, 1), dtype=torch.float32, device=x.device)
-    db = torch.empty((3,), dtype=torch.float32, device=x.device)
+    if dw is None:
+        dw = torch.empty((3, 64, 1, 1), dtype=torch.float32, device=x.device)
+    if db is None:
+        db = torch.empty((3,), dtype=torch.float32, device=x.device)
     call("wu_conv_last_tanh_bprop", ptr(gy), ptr(y), ptr(x), ptr(w), ptr(gx), ptr(dw), ptr(db), B, H,
          W, ptr(ws), nbytes, stream())
     return gx, dw, db
@@ -135,9 +142,10 @@ class AdaINState:
     __slots__ = ("mean", "rstd", "ystd", "scale", "shift", "seed", "mask", "p", "bits")
 
 
-def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False):
+def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False, epoch=None):
     """AdaIN(x, cond) -> bilinear x2 (align_corners) -> dropout.  x (B,h,w,C) -> (B,2h,2w,C).
-    x_bcast: x has batch 1 and serves all cond.shape[0] conditions."""
+    x_bcast: x has batch 1 and serves all cond.shape[0] conditions.
+    epoch: optional device int32 scalar, the draw counter of wu_adain_up_drop_fwd_epoch."""
     Bx, h, w, C = x.shape
     B = cond.shape[0] if x_bcast else Bx
     nc = cond.shape[1]
@@ -155,8 +163,8 @@ def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False):
     u = _act(B, 2 * h, 2 * w, C, x)
     st.bits = (torch.empty((B, 2 * h, 2 * w, C // 8), dtype=torch.uint8, device=dev)
                if st.p > 0 else None)
-    call("wu_adain_up_drop_fwd", ptr(x), ptr(st.scale), ptr(st.shift), ptr(u), ptr(st.bits), B, h, w,
-         C, st.p, st.seed, ptr(mask), int(x_bcast), stream())
+    call("wu_adain_up_drop_fwd_epoch", ptr(x), ptr(st.scale), ptr(st.shift), ptr(u), ptr(st.bits), B, h,
+         w, C, st.p, st.seed, ptr(epoch), ptr(mask), int(x_bcast), stream())
     return u, st
 
 
@@ -176,7 +184,7 @@ def adain_apply(x, cond, lw, lb, eps):
     return out
 
 
-def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
+def adain_up_drop_bwd(gu, x, cond, lw, lb, st, dlw=None, dlb=None):
     """-> (gx masked by relu'(x), dlw [4C][nc], dlb [4C])."""
     B, h, w, C = x.shape
     nc = cond.shape[1]
@@ -188,8 +196,10 @@ def adain_up_drop_bwd(gu, x, cond, lw, lb, st):
          B, h, w, C, st.p, ptr(st.bits), stream())
     kk = torch.empty((5, B, C), dtype=torch.float32, device=dev)  # k1, k2, coef[3]
     gh = torch.empty((B, 4 * C), dtype=torch.float32, device=dev)
-    dlw = torch.empty((4 * C, nc), dtype=torch.float32, device=dev)
-    dlb = torch.empty((4 * C,), dtype=torch.float32, device=dev)
+    if dlw is None:
+        dlw = torch.empty((4 * C, nc), dtype=torch.float32, device=dev)
+    if dlb is None:
+        dlb = torch.empty((4 * C,), dtype=torch.float32, device=dev)
     call("wu_adain_style_bwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), nchunk, ptr(st.ystd),
          ptr(st.mean), ptr(st.rstd), ptr(kk[0]), ptr(kk[1]), ptr(kk[2]), ptr(gh), ptr(dlw), ptr(dlb), B, C,
          nc, h * w, stream())

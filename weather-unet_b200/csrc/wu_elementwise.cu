@@ -654,7 +654,8 @@ __host__ __device__ inline uint32_t dropout_threshold15(float p) {
 }
 __device__ __forceinline__ void philox_keep8(const PhiloxKeys& keys, uint32_t vimg, uint32_t b,
                                              uint32_t k2, uint4& lanes, uint32_t& byte) {
-  // counter = (8-channel vector index inside the image, image index, tag, 0)
+  // counter = (8-channel vector index inside the image, image index | epoch << 16, tag, 0); the
+  // epoch (0 unless the caller keeps a device-side draw counter) is merged into b by the kernel
   const uint4 r = philox4x32(make_uint4(vimg, b, 0x77755555u, 0u), keys);
   const uint32_t s0 = (r.x & 0x7FFF7FFFu) + k2, s1 = (r.y & 0x7FFF7FFFu) + k2;
   const uint32_t s2 = (r.z & 0x7FFF7FFFu) + k2, s3 = (r.w & 0x7FFF7FFFu) + k2;
@@ -735,7 +736,8 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ u,
                          uint8_t* __restrict__ keep_bits, int h, int w, int C, float inv_keep,
                          uint32_t thr, const __grid_constant__ PhiloxKeys keys,
-                         const uint8_t* __restrict__ mask, int xb_mul, float rh, float rw, int cv_shift) {
+                         const uint8_t* __restrict__ mask, int xb_mul, float rh, float rw, int cv_shift,
+                         const uint32_t* __restrict__ epoch) {
   // rh = (h-1)/(2h-1), rw = (w-1)/(2w-1) in fp32 (PyTorch's ratio) and cv_shift = log2(C/8) or -1 come
   // from the host: two fp32 divisions and an integer division per thread were a tenth of the kernel
   const int cv = C >> 3, Ho = 2 * h, Wo = 2 * w;
@@ -744,6 +746,9 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   const int kx = cv_shift >= 0 ? (xi >> cv_shift) : xi / cv;
   const int v = xi - kx * cv;
   const int b = blockIdx.z;
+  // Philox counter word 1: image index (< 65536) | low 16 bits of the device-side draw counter.  The
+  // counter lives in device memory so that a CUDA-graph replay of the same launch draws a NEW mask.
+  const uint32_t ctr_b = (uint32_t)b | ((MODE == kDropPhilox && epoch != nullptr) ? (__ldg(epoch) << 16) : 0u);
   const int j4 = blockIdx.y;  // row group: rows 4j-1 .. 4j+2, j = 0 .. h/2
   const int Y0 = 4 * j4 - 1;
   const size_t img_vecs = (size_t)Ho * Wo * cv;
@@ -814,7 +819,7 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
 #pragma unroll
         for (int i = 2 * pair; i < 2 * pair + 2; ++i)
           if (oky[i])
-            adain_emit<MODE>(H[pair][q], dv, ly[i], (uint32_t)(vi00 + i * vi_row + q * cv), (uint32_t)b, u,
+            adain_emit<MODE>(H[pair][q], dv, ly[i], (uint32_t)(vi00 + i * vi_row + q * cv), ctr_b, u,
                              keep_bits, thr, keys, mask);
       }
     }
@@ -848,7 +853,7 @@ adain_up_drop_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
       sub8(pr, pl, dx);
       lerp8(pl, dx, lxx, hb);
       sub8(hb, ht, dv);
-      adain_emit<MODE>(ht, dv, lyy, (uint32_t)(vi00 + i * vi_row + q * cv), (uint32_t)b, u, keep_bits, thr,
+      adain_emit<MODE>(ht, dv, lyy, (uint32_t)(vi00 + i * vi_row + q * cv), ctr_b, u, keep_bits, thr,
                        keys, mask);
     }
   }
@@ -1259,6 +1264,13 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
                                     uint8_t* keep_bits, int B, int h, int w, int C, float p_drop,
                                     uint64_t seed, const uint8_t* mask, int x_bcast,
                                     wu_stream_t stream) {
+  return wu_adain_up_drop_fwd_epoch(x, scale, shift, u, keep_bits, B, h, w, C, p_drop, seed, nullptr,
+                                    mask, x_bcast, stream);
+}
+extern "C" int wu_adain_up_drop_fwd_epoch(const void* x, const float* scale, const float* shift, void* u,
+                                          uint8_t* keep_bits, int B, int h, int w, int C, float p_drop,
+                                          uint64_t seed, const uint32_t* epoch, const uint8_t* mask,
+                                          int x_bcast, wu_stream_t stream) {
   WU_REQUIRE(x && scale && shift && u && B > 0 && h > 0 && w > 0, "wu_adain_up_drop_fwd: bad args");
   WU_REQUIRE(C > 0 && C % 8 == 0, "wu_adain_up_drop_fwd: C=%d must be a multiple of 8", C);
   WU_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "wu_adain_up_drop_fwd: p_drop=%f out of [0,1)", p_drop);
@@ -1282,15 +1294,15 @@ extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const flo
   if (p_drop == 0.f)
     adain_up_drop_fwd_kernel<kDropNone><<<grid, 256, 0, st>>>(
         (const bf16*)x, scale, shift, (bf16*)u, nullptr, h, w, C, 1.f, 0u, keys, nullptr, xm, rh, rw,
-        cv_shift);
+        cv_shift, nullptr);
   else if (mask != nullptr)
     adain_up_drop_fwd_kernel<kDropInjected><<<grid, 256, 0, st>>>(
         (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep, 1u, keys, mask, xm, rh, rw,
-        cv_shift);
+        cv_shift, nullptr);
   else  // thr argument = (32768 - thr15) in both 16-bit lanes (philox_keep8)
     adain_up_drop_fwd_kernel<kDropPhilox><<<grid, 256, 0, st>>>(
         (const bf16*)x, scale, shift, (bf16*)u, keep_bits, h, w, C, inv_keep,
-        (32768u - dropout_threshold15(p_drop)) * 0x00010001u, keys, nullptr, xm, rh, rw, cv_shift);
+        (32768u - dropout_threshold15(p_drop)) * 0x00010001u, keys, nullptr, xm, rh, rw, cv_shift, epoch);
   WU_CHECK_LAUNCH("adain_up_drop_fwd_kernel");
   return WU_OK;
 }

@@ -59,6 +59,7 @@ class Conditional_UNet(nn.Module):
         self.activation = nn.Tanh()
         self._packed = PackedWeights()  # derived bf16 weights: not parameters, not persistent
         self._grad_sink = None  # data-parallel gradient buckets (train_step.GradBuckets), if any
+        self._drop_seed, self._drop_epoch = 0, None  # see use_device_dropout_counter
 
     def forward(self, x, c, dropout_masks=None, seed=None, _keep_acts=None):
         """x: (B, 3, H, W) float in [-1, 1], H and W divisible by 8; c: (B, num_classes) float.
@@ -69,6 +70,21 @@ class Conditional_UNet(nn.Module):
         ``seed`` = explicit dropout seed.  Dropout follows ``self.training`` like nn.Dropout."""
         return generator_forward(self, x, c, dropout_masks=dropout_masks, seed=seed,
                                  keep_acts=_keep_acts)
+
+    def use_device_dropout_counter(self, enable=True):
+        """Draw the dropout masks (cunet.py:61,68,75) from one base seed (taken from torch's host RNG
+        now) plus a counter that lives on the device and advances with every training forward,
+        instead of one host RNG draw per forward.  Statistically the same stream family; required
+        when forward passes are replayed from a CUDA graph (a host-drawn seed would be frozen into
+        the graph and every replay would reuse one mask).  The 16-bit counter field wraps after
+        65 536 forwards, after which masks repeat with a different image/mask pairing only if the
+        data repeats in lock-step."""
+        if enable:
+            self._drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self._drop_epoch = torch.zeros((), dtype=torch.int32, device=self.conv_last.weight.device)
+        else:
+            self._drop_epoch = None
+        return self
 
     def packed_weight_names(self):
         """Names of the parameters that have derived bf16 operand copies in `self._packed` (what
@@ -82,4 +98,7 @@ class Conditional_UNet(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         self._packed.clear()  # .cuda()/.to() move the master weights: drop derived copies
-        return super()._apply(fn, *args, **kwargs)
+        out = super()._apply(fn, *args, **kwargs)
+        if self._drop_epoch is not None:
+            self._drop_epoch = fn(self._drop_epoch)
+        return out

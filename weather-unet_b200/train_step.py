@@ -125,7 +125,7 @@ class GDTrainStep:
     """
 
     def __init__(self, G, D, lr=1e-4, estimator=None, d_autocast=True, eps_con=1e-2, group=None,
-                 overlap=True, distributed=None, share_fake=False, fused_adam=None):
+                 overlap=True, distributed=None, share_fake=False, fused_adam=None, static_grads=False):
         self.G, self.D, self.estimator = G, D, estimator
         # share_fake=True is NOT the reference's schedule: the reference runs the generator twice per
         # iteration (t_cls_train.py:302 and :242) with two independent dropout draws; sharing one
@@ -144,7 +144,10 @@ class GDTrainStep:
         self.distributed = bool(distributed)
         self.g_buckets = self.d_buckets = None
         self._use_sink = False
-        if self.distributed:
+        # static_grads: keep every .grad at a fixed address (views into flat buckets, written in place
+        # by the generator's backward) even on one GPU — what capturing the iteration in a CUDA
+        # graph needs (GraphedGDStep); it is the data-parallel bookkeeping without the collective
+        if self.distributed or static_grads:
             skip = tuple(n for n, _ in G.named_parameters() if n.endswith("emb.weight"))
             self.g_buckets = GradBuckets(G.named_parameters(), group, skip=skip)
             self.d_buckets = GradBuckets(D.named_parameters(), group)
@@ -155,7 +158,7 @@ class GDTrainStep:
             self._use_sink = bool(overlap and hasattr(G, "_grad_sink"))
             if not self._use_sink:
                 self.g_buckets.attach_autograd_hooks()
-            for m in (G, D):  # identical replicas to start from
+            for m in ((G, D) if self.distributed else ()):  # identical replicas to start from
                 with torch.no_grad():
                     for t in list(m.parameters()) + list(m.buffers()):
                         # detach() shares the version counter (unlike .data): caches keyed on it
@@ -165,9 +168,12 @@ class GDTrainStep:
         if fused_adam is None:
             fused_adam = next(G.parameters()).is_cuda
         if fused_adam:  # same rule, one launch per model (optim.py / wu_adam_multi)
-            from .optim import FusedAdam as Adam
+            from .optim import FusedAdam
+            import functools
+            Adam = functools.partial(FusedAdam, device_step=static_grads)
         else:
             Adam = torch.optim.Adam
+        self.fused_adam = bool(fused_adam)
         self.g_opt = Adam(G.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
         self.d_opt = Adam(D.parameters(), lr=lr, betas=(0.0, 0.999), weight_decay=lr / 20)
         if fused_adam and hasattr(G, "packed_weight_names"):
@@ -256,3 +262,64 @@ class GDTrainStep:
         if g_w is not None:
             out["g_loss_w"] = g_w.detach()
         return out
+
+
+class GraphedGDStep:
+    """The whole training iteration (D update + G update, both Adam steps, the gradient
+    all-reduces when data parallel) captured ONCE in a CUDA graph and replayed per batch: the
+    ~470 kernel launches of an iteration cost one graph launch on the host, and the GPU no longer
+    idles between dependent kernels waiting for the next launch.
+
+    What makes the iteration replayable: static input buffers; every gradient at a fixed address
+    (GDTrainStep(static_grads=True)); the dropout draw counter and Adam's step count on the
+    device (Conditional_UNet.use_device_dropout_counter, optim.FusedAdam(device_step=True)); TMA
+    descriptors and table pointers baked at capture into memory the graph's pool keeps alive.
+    Same arithmetic as GDTrainStep.step (which is what gets captured).
+
+    `warmup` real training iterations run eagerly on the first batch before the capture (they are
+    ordinary updates); the capture pass itself does not execute."""
+
+    def __init__(self, trainer, images, c_real, c_target, warmup=3):
+        if not (trainer.fused_adam and trainer.g_buckets is not None):
+            raise RuntimeError("GraphedGDStep needs GDTrainStep(static_grads=True) (or data parallel) "
+                               "with the fused optimiser")
+        if getattr(trainer.G, "_drop_epoch", None) is None:
+            trainer.G.use_device_dropout_counter(True)
+        self.trainer = trainer
+        self.inputs = tuple(torch.empty_like(t).copy_(t) for t in (images, c_real, c_target))
+        side = torch.cuda.Stream(device=images.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                trainer.step(*self.inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(images.device)
+        from . import _ops as K
+        n0 = K.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = trainer.step(*self.inputs)
+        self.library_launches = K.launch_count() - n0  # launches of this library per replay
+        self._undo_capture_side_effects()
+
+    def _undo_capture_side_effects(self):
+        """The capture pass ran the host side of one iteration without executing it: the host mirrors
+        of the step counts advanced by one although no update happened."""
+        for opt in (self.trainer.g_opt, self.trainer.d_opt):
+            for st in opt.state.values():
+                if "step" in st:
+                    st["step"] -= 1
+
+    def step(self, images=None, c_real=None, c_target=None):
+        """Copy the batch into the static buffers (skip by passing None and writing
+        `self.inputs` yourself, e.g. straight from pinned host memory) and replay.  Returns the
+        static loss tensors (overwritten by the next replay)."""
+        if images is not None:
+            for dst, src in zip(self.inputs, (images, c_real, c_target)):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for opt in (self.trainer.g_opt, self.trainer.d_opt):
+            steps = [st["step"] for st in opt.state.values() if "step" in st]
+            if steps:
+                torch._foreach_add_(steps, 1)
+        return self.outputs
