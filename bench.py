@@ -21,8 +21,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "cunet_gd_train_images_per_sec_256x256"
 UNIT = "images/s"
+
+
+def metric_name(size):
+    return f"cunet_gd_train_images_per_sec_{size}x{size}"
 
 
 def parse():
@@ -37,6 +40,10 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / transfer legs")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the iteration kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--no-comparator", action="store_true",
+                    help="skip the PyTorch/cuDNN same-box comparator and the estimator-plugged step")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -99,6 +106,28 @@ def cpu_train_step_rate(size, nc, batch, steps, warmup):
     return batch * steps / dt, dt / steps, cores
 
 
+def cpu_forward_rate(size, nc, reps=5, warmup=2):
+    """BASELINE configs[0]: generator forward on ONE image with a one-hot condition on the CPU, eval
+    mode (demo.py:52-54,79), random-init weights; oracle restatement, fp32, all host cores."""
+    import torch
+    from oracle import cunet_oracle as O
+    from weather_unet_b200 import Conditional_UNet
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sd = Conditional_UNet(nc).state_dict()
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(1, 3, size, size, generator=g) * 2 - 1
+    c = torch.eye(nc)[:1]
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.forward(sd, x, c, train=False)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.forward(sd, x, c, train=False)
+        dt = time.perf_counter() - t0
+    return reps / dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -109,7 +138,7 @@ def run_reference(args):
     sample = (f"{steps} timed CPU iterations of the oracle restatement of the reference train step "
               f"(fp32, torch CPU) at batch {args.ref_batch}, {args.size}x{args.size}, after {warm} warm-up")
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.size), "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"G+D train step, batch {args.ref_batch} (bounded CPU sample), "
@@ -174,6 +203,85 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# same-box comparators ("the real bar"): the reference's arithmetic through PyTorch + cuDNN
+# ------------------------------------------------------------------------------------------------
+def comparator_legs(args, dev, resident, trainer, G, D):
+    """(i) The oracle trainer — the restatement pinned bit-for-bit to the reference's modules — on
+    THIS GPU through PyTorch 2.x / cuDNN: fp32 with TF32 convolutions (what the unmodified reference
+    gets on an Ampere-or-later GPU) and under torch.autocast(bf16); same batch, CUDA-event timed.
+    (ii) Our iteration with the estimator term plugged in (t_cls_train.py:247-256): a frozen
+    random-init torchvision ResNet-101 (num_classes = nc) through PyTorch, the second number SURVEY
+    §8d asks for."""
+    import torch
+    from oracle import train_oracle as T
+    from weather_unet_b200.train_step import GDTrainStep
+    B, S, nc = args.batch, args.size, args.nc
+    out = {}
+
+    def timed(fn, warm, it):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(it):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / it
+
+    x, cr, ct = resident[0]
+    comp = {}
+    for name, autocast in (("fp32_tf32", False), ("autocast_bf16", True)):
+        try:
+            torch.cuda.empty_cache()
+            tr = T.Trainer({k: v.detach().clone() for k, v in G.state_dict().items()},
+                           {k: v.detach().clone() for k, v in D.state_dict().items()}, lr=1e-4)
+            old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+            xin = x.contiguous(memory_format=torch.channels_last) if autocast else x
+
+            def one():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    tr.step(xin, cr, ct)
+            ms = timed(one, 2, 3)
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+            comp[name] = {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms}
+            del tr
+        except Exception as e:  # report, never fail the headline
+            comp[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    comp["what"] = ("oracle trainer (pinned bit-exact to the reference modules) on this GPU via PyTorch "
+                    f"{torch.__version__} + cuDNN {torch.backends.cudnn.version()}, batch {B}, {S}x{S}, "
+                    "torch.optim.Adam, cudnn.benchmark on, losses read with .item() like the reference; "
+                    "3 timed iterations after 2 warm-up")
+    out["gpu_comparator"] = comp
+    torch.cuda.empty_cache()
+    try:
+        import torchvision
+        torch.manual_seed(5)
+        est = torchvision.models.resnet101(num_classes=nc).to(dev).eval()
+        for p in est.parameters():
+            p.requires_grad_(False)
+        est = est.to(memory_format=torch.channels_last)
+
+        def estimator(img):  # frozen ResNet-101 through PyTorch / cuDNN under bf16 autocast
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return est(img.contiguous(memory_format=torch.channels_last)).float()
+        tr2 = GDTrainStep(G, D, lr=1e-4, estimator=estimator)
+        ms = timed(lambda: tr2.step(x, cr, ct), 3, args.steps)
+        out["estimator_plugged_step"] = {
+            "value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+            "note": "G+D iteration with g_loss_w = MSE(estimator(fake), target) (t_cls_train.py:247-256): "
+                    "frozen random-init torchvision resnet101(num_classes=nc) forward + input-gradient "
+                    "through PyTorch/cuDNN (bf16 autocast, channels_last); launched kernel by kernel"}
+        del tr2, est
+    except Exception as e:
+        out["estimator_plugged_step"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -197,7 +305,8 @@ def run_ours(args):
     G = Conditional_UNet(nc).to(dev).train()
     torch.manual_seed(100)
     D = SNDisc(nc).to(dev).train()
-    trainer = GDTrainStep(G, D, lr=1e-4)
+    use_graph = not args.no_graph
+    trainer = GDTrainStep(G, D, lr=1e-4, static_grads=use_graph)
 
     gen = torch.Generator().manual_seed(1234 + rank)
     n_host = 4  # a small ring of distinct pinned host batches
@@ -224,8 +333,19 @@ def run_ours(args):
 
     # ---- warm-up, then the device-resident timed region
     n_warm = max(5, args.warmup)  # >= 3 required; 5 lets clocks / allocator / cuDNN autotune settle
-    for i in range(n_warm):
-        trainer.step(*resident[i % n_host])
+    graphed = None
+    if use_graph:
+        # the whole iteration as ONE CUDA graph (train_step.GraphedGDStep): n_warm eager iterations,
+        # then the capture; every timed step = copy the batch into the static buffers + one replay
+        from weather_unet_b200.train_step import GraphedGDStep
+        graphed = GraphedGDStep(trainer, *resident[0], warmup=n_warm)
+        run_step = graphed.step
+        for i in range(2):
+            run_step(*resident[i % n_host])
+    else:
+        run_step = trainer.step
+        for i in range(n_warm):
+            trainer.step(*resident[i % n_host])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -236,13 +356,14 @@ def run_ours(args):
         torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
-        losses = trainer.step(*resident[i % n_host])
+        losses = run_step(*resident[i % n_host])
     e1.record()
     barrier()
     if args.profiler_range:
         torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = K.launch_count() - n0
+    # kernels of THIS library per timed region (a graph replay re-launches what the capture recorded)
+    launches = (graphed.library_launches * args.steps) if graphed is not None else K.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total / 1e3)
     last = {k: float(v) for k, v in losses.items()}
@@ -280,7 +401,7 @@ def run_ours(args):
         if i + 1 < args.steps:
             upload(i + 1)
         main_stream.wait_event(ready[k])
-        losses = trainer.step(*slots[k])
+        losses = run_step(*slots[k])
         consumed[k].record(main_stream)
         loss_host[k].copy_(torch.stack([losses["d_loss"], losses["g_loss"]]), non_blocking=True)
         loss_done[k].record(main_stream)
@@ -378,6 +499,8 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "conv3x3_igemm_v2_kernel<64, 4> @ dconv_up1.0 fprop (192->64, "
                 f"{S}x{S}, batch {B})", "achieved": dom["fprop_tflops"], "peak": peak_burst,
                 "unit": "TFLOP/s", "frac": dom["fprop_tflops"] / peak_burst, "traffic": traffic,
+                "traffic_source": "profiles/dominant_kernel_traffic.json (one ncu --set full capture of this "
+                                  "launch; a citation, not measured in this run)",
                 "peak_source": peak_src + ", burst (kernel timed alone)",
                 "all_layers": {k: {"tflops": v[0] / v[1] / 1e9, "frac": v[0] / v[1] / 1e9 / peak_burst}
                                for k, v in tot.items()},
@@ -421,36 +544,88 @@ def run_ours(args):
         ]
         roof["hbm_bound_ops"] = {"peak_gbs": hbm, "peak_source": peak_src, "ops": hbm_ops}
         del dy64, y64, gp64, x128, gu128
-        # ---- batched transfer inference (inf_1year_signals.py:98-107): one image x 1024 signals,
-        # sharded by batch across ranks, no collective; train-mode dropout as the reference runs it
+        # ---- batched transfer inference (inference/inf_1year_signals.py:98-107): one image x 1024
+        # signals, sharded by batch across ranks, no collective; train-mode dropout as the reference
+        # runs it (the script never calls transfer.eval()).  Two numbers per variant: device-resident
+        # (`value`) and end to end (`e2e`): the signals come from pinned host memory and EVERY output
+        # image goes back to pinned host memory (the reference hands each one to save_image), the
+        # device -> host copies running on a copy stream under the next chunk's compute.
         n_sig = 1024
         per_rank = n_sig // world
         img1 = (torch.rand(1, 3, S, S, generator=gen) * 2 - 1).to(dev)
-        sig = torch.randn(per_rank, nc, generator=gen).to(dev)
+        sig_host = torch.randn(per_rank, nc, generator=gen).pin_memory()
+        sig = sig_host.to(dev)
         chunk = min(128, per_rank)
         rep = img1.repeat(chunk, 1, 1, 1)  # materialised copies, as the reference's DataLoader collates
+        out_host = torch.empty((per_rank, 3, S, S), dtype=torch.float32).pin_memory()
+        d2h_stream = torch.cuda.Stream(device=dev)
+        n_chunks = (per_rank + chunk - 1) // chunk
+        out_slots = [torch.empty((chunk, 3, S, S), dtype=torch.float32, device=dev) for _ in range(2)]
+        slot_free = [torch.cuda.Event() for _ in range(2)]
+        reps_tr = 10
 
-        def transfer(dedup):
+        def transfer(dedup, e2e):
             with torch.no_grad():
-                for j in range(0, per_rank, chunk):
+                for ci, j in enumerate(range(0, per_rank, chunk)):
                     n = min(chunk, per_rank - j)
-                    G(img1 if dedup else rep[:n], sig[j:j + n])
+                    if e2e:
+                        sg = sig_host[j:j + n].to(dev, non_blocking=True)
+                        main_stream.wait_event(slot_free[ci % 2])
+                    else:
+                        sg = sig[j:j + n]
+                    y = G(img1 if dedup else rep[:n], sg)
+                    if e2e:
+                        out_slots[ci % 2][:n].copy_(y)
+                        done = torch.cuda.Event()
+                        done.record(main_stream)
+                        with torch.cuda.stream(d2h_stream):
+                            d2h_stream.wait_event(done)
+                            out_host[j:j + n].copy_(out_slots[ci % 2][:n], non_blocking=True)
+                            slot_free[ci % 2].record(d2h_stream)
+            if e2e:
+                main_stream.wait_stream(d2h_stream)
 
+        # tensor-core work of one transfer image (forward only): full generator, or decoder + the
+        # per-condition half of the concat convolutions when the encoder is shared
+        gf_img = g_conv_flops(S, S)
+        enc = sum(2 * 9 * ci * co * (S // d) * (S // d) for ci, co, d in
+                  [(3, 64, 1), (64, 64, 1), (64, 128, 2), (128, 128, 2), (128, 256, 4), (256, 256, 4),
+                   (256, 512, 8), (512, 512, 8)])
         for key, dedup in (("transfer", False), ("transfer_dedup", True)):
-            transfer(dedup)
-            barrier()
-            e0.record()
-            for _ in range(3):
-                transfer(dedup)
-            e1.record()
-            barrier()
-            ms_tr = max_over_ranks(e0.elapsed_time(e1)) / 3
+            res = {}
+            for e2e in (False, True):
+                for ev in slot_free:
+                    ev.record(d2h_stream)
+                transfer(dedup, e2e)
+                barrier()
+                e0.record()
+                for _ in range(reps_tr):
+                    transfer(dedup, e2e)
+                e1.record()
+                barrier()
+                res[e2e] = max_over_ranks(e0.elapsed_time(e1)) / reps_tr
+            rate = n_sig / (res[False] / 1e3)
             extras[key] = {
-                "metric": "batched_transfer_images_per_sec_256x256", "value": n_sig / (ms_tr / 1e3),
-                "unit": UNIT, "signals": n_sig,
+                "metric": f"batched_transfer_images_per_sec_{S}x{S}", "value": rate,
+                "unit": UNIT, "signals": n_sig, "reps": reps_tr, "ms_per_sweep": res[False],
+                "e2e": {"value": n_sig / (res[True] / 1e3), "unit": UNIT,
+                        "h2d_bytes_per_sweep": per_rank * nc * 4 * world,
+                        "d2h_bytes_per_sweep": per_rank * 3 * S * S * 4 * world,
+                        "ms_per_sweep": res[True]},
+                "tensor_roofline": {
+                    "executed_conv_tflops": (gf_img * rate if not dedup else
+                                             ((gf_img - enc) * rate + enc * rate / chunk)) / 1e12,
+                    "faithful_conv_tflops": gf_img * rate / 1e12,
+                    "frac_of_sustained_peak": (gf_img * rate if not dedup else
+                                               ((gf_img - enc) * rate + enc * rate / chunk)) / 1e12 / world
+                    / peak_sust},
                 "mode": ("train-mode dropout (faithful), sharded by batch, no collective; " +
                          ("encoder and skip tensors computed once per image (SURVEY §8 f3), "
                           "bit-identical output" if dedup else "replicated image batch, full compute"))}
+        del out_host, out_slots
+
+    if not args.no_extras and not args.no_comparator and world == 1:
+        extras.update(comparator_legs(args, dev, resident, trainer, G, D))
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -458,7 +633,11 @@ def run_ours(args):
         rate, sec, cores = cpu_train_step_rate(S, nc, args.ref_batch, n_cpu, 1)
         cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{n_cpu} timed CPU iterations (1 warm-up) of the oracle restatement of the "
-                              f"reference train step, fp32 torch CPU, batch {args.ref_batch}, {S}x{S}"}
+                              f"reference train step, fp32 torch CPU, batch {args.ref_batch}, {S}x{S}",
+                    "config1_forward": {
+                        "value": cpu_forward_rate(S, nc), "unit": UNIT,
+                        "what": "BASELINE configs[0]: generator forward, ONE image, one-hot condition, "
+                                "eval mode (demo.py:52-54,79), fp32 torch CPU, mean of 5 after 2 warm-up"}}
 
     if rank == 0:
         gf, df = g_conv_flops(S, S), d_conv_flops(S, S)
@@ -468,7 +647,7 @@ def run_ours(args):
                         + 3 * df                                # 3 D forward
                         + 5 * df)                               # 2 D full backward + 1 dgrad-only
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(S), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -477,6 +656,8 @@ def run_ours(args):
                        "per_gpu_batch": B, "global_batch": B * world, "image": f"{S}x{S}",
                        "parallelism": f"dp{world}",
                        "l2": "inputs and activations (GBs per step) far exceed the 126 MB L2; no flush",
+                       "launch": ("one CUDA graph replay per iteration (train_step.GraphedGDStep)"
+                                  if graphed is not None else "kernel by kernel"),
                        "generator": "sm_100a kernels (this repo)",
                        "discriminator": "sm_100a kernels (this repo; bf16 activations, fp32 spectral norm), "
                                         "512-wide projection head on PyTorch"},
@@ -484,9 +665,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "step_tflops": {"executed_conv_flops_per_step": executed,
-                            "achieved": executed * args.steps / (ms_total / 1e3) / 1e12 / world,
+                            # `executed` is per GPU and every GPU runs its own step: per-GPU rate
+                            "achieved": executed * args.steps / (ms_total / 1e3) / 1e12,
                             "frac_of_sustained_peak": executed * args.steps / (ms_total / 1e3) / 1e12
-                            / world / peak_sust,
+                            / peak_sust,
                             "reference_faithful_flops_per_step": flops_step},
             "losses_last_step": last,
         }
