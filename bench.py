@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / transfer legs")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch the iteration kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="ablation for the scaling analysis: skip the gradient all-reduces (replicas drift)")
     ap.add_argument("--no-comparator", action="store_true",
                     help="skip the PyTorch/cuDNN same-box comparator and the estimator-plugged step")
     ap.add_argument("--profiler-range", action="store_true",
@@ -307,6 +309,8 @@ def run_ours(args):
     D = SNDisc(nc).to(dev).train()
     use_graph = not args.no_graph
     trainer = GDTrainStep(G, D, lr=1e-4, static_grads=use_graph)
+    if args.no_allreduce and trainer.g_buckets is not None:
+        trainer.g_buckets.collective = trainer.d_buckets.collective = False
 
     gen = torch.Generator().manual_seed(1234 + rank)
     n_host = 4  # a small ring of distinct pinned host batches
@@ -331,6 +335,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_ranks(v):
+        if world == 1:
+            return [v]
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = v
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
     # ---- warm-up, then the device-resident timed region
     n_warm = max(5, args.warmup)  # >= 3 required; 5 lets clocks / allocator / cuDNN autotune settle
     graphed = None
@@ -340,7 +352,7 @@ def run_ours(args):
         from weather_unet_b200.train_step import GraphedGDStep
         graphed = GraphedGDStep(trainer, *resident[0], warmup=n_warm)
         run_step = graphed.step
-        for i in range(2):
+        for i in range(3):
             run_step(*resident[i % n_host])
     else:
         run_step = trainer.step
@@ -348,8 +360,7 @@ def run_ours(args):
             trainer.step(*resident[i % n_host])
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()  # every rank samples its own GPU; rank 0's goes into `clocks`, all into `per_rank`
     n0 = K.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.profiler_range:
@@ -361,10 +372,14 @@ def run_ours(args):
     barrier()
     if args.profiler_range:
         torch.cuda.profiler.stop()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_own = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_own)
+    clocks = sampler.stop()
+    per_rank = {"ms_per_step": [round(v / args.steps, 3) for v in gather_ranks(ms_own)],
+                "sm_mhz": gather_ranks(float(clocks.get("sm_mhz") or 0.0)),
+                "power_w_max": gather_ranks(float(clocks.get("power_w_max") or 0.0))}
     # kernels of THIS library per timed region (a graph replay re-launches what the capture recorded)
     launches = (graphed.library_launches * args.steps) if graphed is not None else K.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total / 1e3)
     last = {k: float(v) for k, v in losses.items()}
 
@@ -654,14 +669,15 @@ def run_ours(args):
             "config": {"workload": f"cUNet G + SNDisc D training iteration (t_cls_train.py supervised "
                                    f"branch, estimator term omitted), batch {B}/GPU, {S}x{S}, nc={nc}",
                        "per_gpu_batch": B, "global_batch": B * world, "image": f"{S}x{S}",
-                       "parallelism": f"dp{world}",
+                       "parallelism": f"dp{world}" + (" (ABLATION: gradient all-reduce disabled)"
+                                                      if args.no_allreduce else ""),
                        "l2": "inputs and activations (GBs per step) far exceed the 126 MB L2; no flush",
                        "launch": ("one CUDA graph replay per iteration (train_step.GraphedGDStep)"
                                   if graphed is not None else "kernel by kernel"),
                        "generator": "sm_100a kernels (this repo)",
                        "discriminator": "sm_100a kernels (this repo; bf16 activations, fp32 spectral norm), "
                                         "512-wide projection head on PyTorch"},
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "per_rank": per_rank, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "step_tflops": {"executed_conv_flops_per_step": executed,

@@ -81,14 +81,21 @@ def test_fused_spectral_norm(cuda):
 
 def test_disc_fast_path(cuda):
     """SNDisc under bf16 autocast on an fp32 NCHW image runs entirely on the sm_100a kernels (fused
-    spectral norm, stem, tcgen05 trunk); outputs, gradients and the spectral-norm buffers agree with
-    the plain PyTorch module path in the same precision."""
+    spectral norm, stem, tcgen05 trunk).  Output, every parameter gradient and the spectral-norm
+    buffers are checked against the fp32 ORACLE (oracle/train_oracle.disc_forward, pinned bit-exact
+    to the reference's disc.py:27-38), with stock PyTorch bf16 autocast of the same modules run
+    alongside as the error band a bf16 discriminator has against fp32."""
+    from oracle import train_oracle as T
     from weather_unet_b200.disc import SNDisc
     from weather_unet_b200 import _ops as K
     torch.manual_seed(100)
     d1 = SNDisc(5).to(cuda).train()
     torch.manual_seed(100)
     d2 = SNDisc(5).to(cuda).train().to(memory_format=torch.channels_last)
+    sd = {k: v.detach().clone() for k, v in d1.state_dict().items()}
+    for k in sd:
+        if k.endswith("_orig") or k.endswith("bias"):
+            sd[k].requires_grad_(True)
     x = torch.rand(4, 3, 64, 64, device=cuda) * 2 - 1
     c = torch.eye(5, device=cuda)[:4]
     n0 = K.launch_count()
@@ -99,21 +106,33 @@ def test_disc_fast_path(cuda):
     assert K.launch_count() - n0 >= 4 + 2 + 3 * 2, "kernel path not taken"
     assert [tuple(f.shape) for f in res[1:]] == [(4, 64, 32, 32), (4, 128, 16, 16), (4, 256, 8, 8), (4, 512, 4, 4)]
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        h = x.contiguous(memory_format=torch.channels_last)
-        for i in range(1, 5):
-            h = getattr(d2, f"conv{i}")(h)  # plain nn.Sequential path (cuDNN)
-        pooled = h.sum(dim=(2, 3))
-        o2 = (d2.l(pooled) + (d2.embed(c) * pooled).sum(1, keepdim=True)).float()
-    assert torch.allclose(o1, o2, rtol=3e-2, atol=3e-2 * o2.abs().max().item())
-    for (n, b1), (_, b2) in zip(d1.named_buffers(), d2.named_buffers()):
-        assert torch.allclose(b1, b2, rtol=2e-2, atol=2e-3), n  # d2's power iteration ran in bf16
+        o2 = d2(x.contiguous(memory_format=torch.channels_last), c)[0].float()  # plain modules (cuDNN bf16)
+    ref = T.disc_forward(sd, x, c, train=True)  # fp32, TF32 off (conftest)
+    o_ref = ref[0]
+    scale = o_ref.abs().max().item()
+    e1 = (o1 - o_ref).abs().max().item() / scale
+    e2 = (o2 - o_ref).abs().max().item() / scale
+    print(f"output vs fp32 oracle: kernels {e1:.2e}, cuDNN autocast {e2:.2e}")
+    assert e1 < 2e-2 and e1 < 2 * e2 + 5e-3
+    for f1, fr in zip(res[1:], ref[1:]):  # the feature maps the reference also returns
+        assert ((f1.float() - fr).norm() / fr.norm()).item() < 1.5e-2
+    for n, b1 in d1.named_buffers():  # power iteration ran in fp32 here, like the oracle's
+        assert torch.allclose(b1, sd[n], rtol=1e-4, atol=1e-6), n
     o1.sum().backward()
     o2.sum().backward()
+    o_ref.sum().backward()
+    worst = 0.0
     for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
-        r = ((p.grad.float() - q.grad.float()).norm() / (q.grad.float().norm() + 1e-12)).item()
-        # two bf16 pipelines that round at different points (conv output vs conv output + bias):
-        # 1e-2 on the late layers, up to ~7e-2 on the first (deepest) convolution
-        assert r < 1e-1, f"{n}: {r}"
+        g = sd[n].grad
+        r1 = ((p.grad.float() - g).norm() / (g.norm() + 1e-12)).item()
+        r2 = ((q.grad.float() - g).norm() / (g.norm() + 1e-12)).item()
+        cos = (p.grad.float().flatten() @ g.flatten() / (p.grad.float().norm() * g.norm() + 1e-30)).item()
+        print(f"   {n:28s} rel-L2 vs fp32 oracle: kernels {r1:.3e}  cuDNN autocast {r2:.3e}  cos {cos:.5f}")
+        worst = max(worst, r1)
+        # parameter-gradient rel-L2 <= 3e-2 and cosine >= 0.999 vs fp32; a LeakyReLU
+        # network has no dead units, so (unlike the generator) the bound holds end to end
+        assert r1 < 3e-2 and cos > 0.999, f"{n}: rel-L2 {r1}, cos {cos}"
+        assert r1 < 2 * r2 + 5e-3, f"{n}: kernels {r1} vs autocast band {r2}"
 
 
 @pytest.mark.parametrize("d_kernels", [False, True])

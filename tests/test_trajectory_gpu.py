@@ -293,3 +293,45 @@ def test_graphed_step_matches_eager(cuda):
         wf, wd = Gb._packed.buffers(n, w)
         rf, rd = K.pack_conv3x3_weights(w)
         assert torch.equal(wf, rf) and torch.equal(wd, rd), n
+
+
+def test_dp_gradient_sink_on_nccl_group_of_one(cuda):
+    """The data-parallel machinery on real hardware: GDTrainStep(distributed=True) on a one-rank NCCL
+    group — flat buckets, the generator's backward writing each gradient into its bucket slot and
+    firing the bucket's ncclAllReduce(AVG) on the side stream, the discriminator's autograd hooks,
+    finish() — must leave exactly the parameters the plain single-GPU path leaves."""
+    import torch.distributed as dist
+    from weather_unet_b200.train_step import GDTrainStep
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    g = torch.Generator().manual_seed(31)
+    x = (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).to(cuda)
+    cr = torch.eye(5)[torch.randint(0, 5, (2,), generator=g)].to(cuda)
+    ct = torch.eye(5)[torch.randint(0, 5, (2,), generator=g)].to(cuda)
+
+    def run(distributed):
+        G, D = _mk(cuda)
+        G.use_device_dropout_counter(True)
+        G._drop_seed = 777
+        t = GDTrainStep(G, D, lr=1e-3, distributed=distributed)
+        losses = [{k: float(v) for k, v in t.step(x, cr, ct).items()} for _ in range(3)]
+        return G, D, t, losses
+
+    Ga, Da, ta, la = run(False)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=1, rank=0,
+                            device_id=cuda)
+    try:
+        Gb, Db, tb, lb = run(True)
+        assert tb.distributed and tb._use_sink and tb.g_buckets.collective
+        assert all(tb.g_buckets.launched) and all(tb.d_buckets.launched), "a bucket was never reduced"
+        assert Gb._grad_sink is None, "the sink must not stay attached outside step()"
+        torch.cuda.synchronize()
+    finally:
+        dist.destroy_process_group()
+    assert la == lb, (la, lb)
+    for (n, p), (_, q) in zip(list(Ga.named_parameters()) + list(Da.named_parameters()),
+                              list(Gb.named_parameters()) + list(Db.named_parameters())):
+        assert torch.equal(p, q), n

@@ -364,40 +364,38 @@ struct ConvParams2 {
   __nv_bfloat16* pool_dst;
 };
 
-// ABOX = 1 (WU_CONV_IMPL=3/4, not the default yet): ONE TMA box (64 ch, 10 px, 16T+2 rows) per channel
-// block serves all nine taps — tap (r, s) starts r * 1280 + s * 128 bytes into it and its 8-pixel row
-// groups are 1280 bytes apart.  The tensor core applies the 128-byte swizzle to the absolute
-// shared-memory address, so such starts read correctly (tools/scratch/umma_unaligned_probe.cu,
-// profiles/r01_umma_unaligned_start_probe.txt): 1.25x instead of 3x the tile's bytes cross L2 -> SM.
-// A stage is then recycled per channel block, not per column shift.
-template <int BN, int T, int ABOX = 0>
+// (A variant that loads ONE 10-pixel-wide TMA box per channel block and reaches the three column
+// shifts through 128-byte start offsets — UMMA operands may start at any 128-byte boundary under
+// SWIZZLE_128B, profiles/r01_umma_unaligned_start_probe.txt — was validated and timed in round 2:
+// bit-identical results, 2.4x fewer bytes across L2 -> SM, and no faster (fprop 73.0 vs 73.2 % of peak
+// over the 13 layers, dgrad 69.1 vs 70.9 %): these kernels are paced by the tensor core's own
+// shared-memory operand reads, not by the fabric.  Removed; numbers in profiles/r02_conv_impl_*.txt.)
+template <int BN, int T>
 struct ConvCfg2 {
   static constexpr int kARows = 16 * T + 2;
-  static constexpr int kRowPitch = ABOX ? 1280 : 1024;  // bytes per image row of an A stage
+  static constexpr int kRowPitch = 1024;  // bytes per image row of an A stage (8 px x 128 B)
   static constexpr int kATx = kARows * kRowPitch;       // bytes one TMA box delivers
   static constexpr int kABytes = (kATx + 1023) / 1024 * 1024;  // stage stride (1024-byte aligned)
-  static constexpr int kSA = ABOX ? ((BN == 64 && T == 2) ? 3 : 2) : ((T == 4) ? 2 : 3);
-  static constexpr int kSB =
-      ABOX ? (BN == 64 ? (T == 4 ? 3 : 5) : 4) : (BN == 64 ? 5 : (BN == 128 ? 4 : 3));
+  static constexpr int kSA = (T == 4) ? 2 : 3;
+  static constexpr int kSB = BN == 64 ? 5 : (BN == 128 ? 4 : 3);
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kNStg = (ABOX && BN == 64 && T == 4) ? 1 : 2;  // epilogue staging buffers
+  static constexpr int kNStg = 2;  // epilogue staging buffers
   static constexpr int kStagingBytes = kNStg * 16384;
   static constexpr int kMaskBytes = 16384;  // dgrad: ReLU-mask tile of the next chunk (cp.async)
   static constexpr int kSmemBytes =
       kSA * kABytes + kSB * kBBytes + kStagingBytes + kMaskBytes + 1024 + 1024;
   static constexpr uint32_t kTmemCols = 2 * T * BN;
-  static_assert(kTmemCols == 512 || (ABOX && kTmemCols == 256),
-                "TMEM budget: 2 x T x BN must be 512 columns (256 for the ABOX T = 2 variant)");
+  static_assert(kTmemCols == 512, "TMEM budget: 2 x T x BN must be 512 columns");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int T, bool LAST, bool POOL, int ABOX>
+template <int BN, int T, bool LAST, bool POOL>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
                         const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmD, const ConvParams2 p) {
-  using Cfg = ConvCfg2<BN, T, ABOX>;
+  using Cfg = ConvCfg2<BN, T>;
   constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -476,8 +474,8 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
         decode(tile, b, h0, w0, n0);
         for (int cb = 0; cb < p.ctot_blocks; ++cb) {
           for (int s = 0; s < 3; ++s) {
-            if (!ABOX || s == 0) {  // ABOX: one 10-pixel-wide box per channel block
-              const int wl = ABOX ? w0 - 1 : w0 + s - 1;
+            {
+              const int wl = w0 + s - 1;
               mbar_wait(emptyA(sa), pa ^ 1u);
               mbar_arrive_expect_tx(fullA(sa), Cfg::kATx);
               if (cb < p.c0_blocks)
@@ -517,13 +515,9 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
         const uint32_t d_tmem = tmem_base + buf * (T * BN);
         for (int cb = 0; cb < p.ctot_blocks; ++cb) {
           for (int s = 0; s < 3; ++s) {
-            if (!ABOX || s == 0) {
-              mbar_wait(fullA(sa), pa);
-              tc_fence_after();
-            }
-            // ABOX: the column shift is a 128-byte start offset into the one box of this channel block
-            const uint64_t adesc_s =
-                adesc0 + (uint64_t)((sa * Cfg::kABytes + (ABOX ? s * 128 : 0)) >> 4);
+            mbar_wait(fullA(sa), pa);
+            tc_fence_after();
+            const uint64_t adesc_s = adesc0 + (uint64_t)((sa * Cfg::kABytes) >> 4);
             for (int r = 0; r < 3; ++r) {
               mbar_wait(fullB(sb), pb);
               tc_fence_after();
@@ -542,10 +536,8 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
               umma_commit(emptyB(sb));
               if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
-            if (!ABOX || s == 2) {
-              umma_commit(emptyA(sa));
-              if (++sa == SA) { sa = 0; pa ^= 1u; }
-            }
+            umma_commit(emptyA(sa));
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
         }
         umma_commit(tfull_bar(buf));
@@ -712,35 +704,31 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN, int T, bool LAST = false, bool POOL = false, int ABOX = 0>
+template <int BN, int T, bool LAST = false, bool POOL = false>
 static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
                         const CUtensorMap& dm, const ConvParams2& p, cudaStream_t st) {
-  using Cfg = ConvCfg2<BN, T, ABOX>;
+  using Cfg = ConvCfg2<BN, T>;
   static bool attr_done = false;
   if (!attr_done) {
-    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST, POOL, ABOX>,
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST, POOL>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv3x3_igemm_v2_kernel<BN, T, LAST, POOL, ABOX>
+  conv3x3_igemm_v2_kernel<BN, T, LAST, POOL>
       <<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_v2_kernel");
   return WU_OK;
 }
 
-// WU_CONV_IMPL: 0 / unset = per-shape choice, 1 = v1 everywhere, 2 = v2 everywhere (read once);
-// 3 / 4 = experimental one-box A loading for cout % 256 != 0 (ConvCfg2<.., ABOX = 1>; 3: T = 4 at
-// N = 64 with one staging buffer and three weight stages, 4: T = 2 at N = 64) — written at the end of
-// round 1 after the probe, NOT yet run on a GPU: validate with
-//   tools/check_conv_impl.sh   (parity tests, per-layer timings and one bench step under each setting;
-//   3 also covers the fused last / pool layers, 4 leaves those on the default kernel)
+// WU_CONV_IMPL: 0 / unset = per-shape choice, 1 = v1 everywhere, 2 = v2 everywhere (read once; A/B
+// measurements only)
 static int conv_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WU_CONV_IMPL");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 4) v = 0;
+    if (v < 0 || v > 2) v = 0;
   }
   return v;
 }
@@ -1479,10 +1467,9 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
   WU_REQUIRE(cout > 0 && cout % 64 == 0 && cout != 192 && (cout <= 256 || cout % 256 == 0),
              "wu_conv3x3_fprop: cout=%d must be 64, 128 or a multiple of 256", cout);
   const int bn = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
-  const int abox = (conv_impl() >= 3 && bn < 256) ? conv_impl() : 0;
-  if (conv_impl() == 2 || abox || (conv_impl() == 0 && bn < 256)) {
-    const int T = bn == 64 ? (abox == 4 ? 2 : 4) : (bn == 128 ? 2 : 1);
-    const int bw = abox ? 10 : 8;  // pixels per row of an A box
+  if (conv_impl() == 2 || (conv_impl() == 0 && bn < 256)) {
+    const int T = bn == 64 ? 4 : (bn == 128 ? 2 : 1);
+    const int bw = 8;  // pixels per row of an A box
     ConvParams2 q;
     q.c0_blocks = c0 / 64;
     q.ctot_blocks = (c0 + c1) / 64;
@@ -1515,11 +1502,6 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * (c0 + c1), bn)) != WU_OK) return rc;
     if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, 8, 16)) != WU_OK) return rc;
     cudaStream_t st2 = (cudaStream_t)stream;
-    if (abox) {
-      if (bn == 128) return launch_conv2<128, 2, false, false, 1>(a0, a1, bm, dm, q, st2);
-      return abox == 4 ? launch_conv2<64, 2, false, false, 1>(a0, a1, bm, dm, q, st2)
-                       : launch_conv2<64, 4, false, false, 1>(a0, a1, bm, dm, q, st2);
-    }
     switch (bn) {
       case 64: return launch_conv2<64, 4>(a0, a1, bm, dm, q, st2);
       case 128: return launch_conv2<128, 2>(a0, a1, bm, dm, q, st2);
@@ -1571,7 +1553,6 @@ extern "C" int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_pac
   WU_REQUIRE(B > 0 && H > 0 && W > 0, "wu_conv3x3_fprop_last: bad shape B=%d H=%d W=%d", B, H, W);
   WU_REQUIRE(cin > 0 && cin % 64 == 0, "wu_conv3x3_fprop_last: cin=%d must be a positive multiple of 64", cin);
   constexpr int T = 4;
-  const bool abox = conv_impl() == 3;  // experimental one-box A loading (see conv_impl())
   ConvParams2 q;
   q.c0_blocks = q.ctot_blocks = cin / 64;
   q.tiles_w = (W + 7) / 8;
@@ -1594,10 +1575,9 @@ extern "C" int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_pac
   q.pool_dst = nullptr;
   CUtensorMap a0, bm, dm;
   int rc;
-  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, abox ? 10 : 8, 16 * T + 2)) != WU_OK) return rc;
+  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
   if ((rc = make_mat_tmap(&bm, w_packed, 64, 9 * cin, 64)) != WU_OK) return rc;
   if ((rc = make_act_tmap(&dm, dst, B, H, W, 64, 64, 8, 16)) != WU_OK) return rc;
-  if (abox) return launch_conv2<64, T, true, false, 1>(a0, a0, bm, dm, q, (cudaStream_t)stream);
   return launch_conv2<64, T, true>(a0, a0, bm, dm, q, (cudaStream_t)stream);
 }
 
@@ -1610,7 +1590,6 @@ extern "C" int wu_conv3x3_fprop_pool(const void* src, int cin, const void* w_pac
   WU_REQUIRE(cin > 0 && cin % 64 == 0, "wu_conv3x3_fprop_pool: cin=%d must be a positive multiple of 64", cin);
   WU_REQUIRE(cout == 64 || cout == 128, "wu_conv3x3_fprop_pool: cout=%d must be 64 or 128", cout);
   const int T = cout == 64 ? 4 : 2;
-  const bool abox = conv_impl() == 3;  // experimental one-box A loading (see conv_impl())
   ConvParams2 q;
   q.c0_blocks = q.ctot_blocks = cin / 64;
   q.tiles_w = (W + 7) / 8;
@@ -1632,13 +1611,10 @@ extern "C" int wu_conv3x3_fprop_pool(const void* src, int cin, const void* w_pac
   q.pool_dst = (__nv_bfloat16*)pool_dst;
   CUtensorMap a0, bm, dm;
   int rc;
-  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, abox ? 10 : 8, 16 * T + 2)) != WU_OK) return rc;
+  if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
   if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * cin, cout)) != WU_OK) return rc;
   if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, 8, 16)) != WU_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (abox)
-    return cout == 64 ? launch_conv2<64, 4, false, true, 1>(a0, a0, bm, dm, q, st)
-                      : launch_conv2<128, 2, false, true, 1>(a0, a0, bm, dm, q, st);
   return cout == 64 ? launch_conv2<64, 4, false, true>(a0, a0, bm, dm, q, st)
                     : launch_conv2<128, 2, false, true>(a0, a0, bm, dm, q, st);
 }

@@ -25,9 +25,11 @@ class GradBuckets:
     produced.  Parameters whose gradient never arrives (adain*.emb.weight, utils.py:32) are left
     out by passing `skip`."""
 
-    def __init__(self, named_params, group=None, bucket_bytes=8 << 20, skip=()):
+    def __init__(self, named_params, group=None, bucket_bytes=8 << 20, skip=(), collective=None):
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        # collective: run the all-reduce even in a group of one (tests of the launch / stream logic)
+        self.collective = (self.world > 1) if collective is None else bool(collective)
         params = [(n, p) for n, p in named_params if p.requires_grad and n not in skip]
         params.reverse()  # gradients are produced in reverse forward order
         self.buckets, cur, cur_bytes = [], [], 0
@@ -89,7 +91,7 @@ class GradBuckets:
             self._launch(bi)
 
     def _launch(self, bi):
-        if self.launched[bi] or self.world == 1:
+        if self.launched[bi] or not self.collective:
             return
         self.launched[bi] = True
         flat = self.flat[bi]
@@ -108,7 +110,7 @@ class GradBuckets:
         for the outstanding reductions.  Call before optimizer.step()."""
         for bi in range(len(self.buckets)):
             self._launch(bi)
-        if self.comm_stream is not None and self.world > 1:
+        if self.comm_stream is not None and self.collective:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         for bucket in self.buckets:  # no gradient this pass -> grad None, as without data parallelism
             for n, p in bucket:      # (the optimiser then skips it: no weight-decay-only update)
@@ -149,8 +151,9 @@ class GDTrainStep:
         # graph needs (GraphedGDStep); it is the data-parallel bookkeeping without the collective
         if self.distributed or static_grads:
             skip = tuple(n for n, _ in G.named_parameters() if n.endswith("emb.weight"))
-            self.g_buckets = GradBuckets(G.named_parameters(), group, skip=skip)
-            self.d_buckets = GradBuckets(D.named_parameters(), group)
+            coll = self.distributed and dist.is_available() and dist.is_initialized()
+            self.g_buckets = GradBuckets(G.named_parameters(), group, skip=skip, collective=coll)
+            self.d_buckets = GradBuckets(D.named_parameters(), group, collective=coll)
             self.d_buckets.attach_autograd_hooks()
             # the generator's backward writes its gradients straight into the buckets; the sink is
             # handed to the module only around the G update's forward (step()), so a backward
