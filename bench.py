@@ -695,7 +695,17 @@ def run_ours(args):
         line.update(extras)
         emit(line)
     if world > 1:
+        # A captured graph that contains NCCL kernels keeps the communicator busy on teardown (seen:
+        # destroy_process_group() never returning at N = 2).  The JSON line is out; release the graph
+        # first, and never let teardown outlive a few seconds.
+        import threading
+        threading.Timer(15.0, lambda: os._exit(0)).start()
+        graphed = None
+        run_step = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 _JSON_FD = None
