@@ -152,3 +152,61 @@ def test_512_forward_backward_against_oracle(cuda):
                     continue
                 gn, rn = p.grad.float().norm().item(), leaf[name].grad.float().norm().item()
                 assert abs(gn - rn) / rn < 0.15, f"{name}: |g| {gn} vs oracle {rn}"
+
+
+def test_pipeline_repeatability_under_contention(cuda):
+    """Race hunting without compute-sanitizer (closed on the GPU pool, profiles/
+    r02_compute_sanitizer_unavailable.txt): a missing fence or a stage recycled too early in the
+    TMA -> tcgen05 -> epilogue pipelines shows up as run-to-run differences once timing is
+    perturbed.  Every kernel family runs 12 times on the same inputs while a second stream hammers
+    HBM / L2 with copies of varying size; all results must be bit-identical to the first."""
+    from weather_unet_b200 import _ops as K
+    g = torch.Generator().manual_seed(5)
+
+    def bf(*shape):
+        return torch.randn(*shape, generator=g).to(cuda).to(torch.bfloat16)
+
+    noise_src = torch.empty(96 << 20, dtype=torch.uint8, device=cuda)
+    noise_dst = torch.empty_like(noise_src)
+    side = torch.cuda.Stream(device=cuda)
+    cases = []
+    for cin, c1, cout, h in ((64, 0, 64, 96), (128, 64, 64, 64), (128, 0, 128, 48), (256, 128, 256, 24)):
+        s0, s1 = bf(3, h, h, cin), (bf(3, h, h, c1) if c1 else None)
+        dy = bf(3, h, h, cout)
+        wf, wd = K.pack_conv3x3_weights((torch.randn(cout, cin + c1, 3, 3, generator=g) * 0.05).to(cuda))
+        bias = torch.randn(cout, generator=g).to(cuda)
+        cases.append((f"fprop {cin}+{c1}->{cout}", lambda s0=s0, s1=s1, wf=wf, bias=bias, cout=cout:
+                      [K.conv3x3(s0, s1, wf, bias, True, None, cout)]))
+        if not c1:
+            cases.append((f"dgrad {cout}->{cin}", lambda dy=dy, wd=wd, s0=s0, cin=cin:
+                          [K.conv3x3(dy, None, wd, None, False, s0, cin)]))
+        cases.append((f"wgrad {cin}+{c1}->{cout}", lambda s0=s0, s1=s1, dy=dy:
+                      list(K.conv3x3_wgrad(s0, s1, dy))))
+    x128 = bf(3, 24, 24, 128)
+    cond = torch.randn(3, 5, generator=g).to(cuda)
+    lw, lb = (torch.randn(512, 5, generator=g) * 0.3).to(cuda), torch.zeros(512, device=cuda)
+    gu = bf(3, 48, 48, 128)
+    u0, st0 = K.adain_up_drop(x128, cond, lw, lb, 1e-5, 0.3, 9, None)
+    cases.append(("adain_up_drop fwd", lambda: [K.adain_up_drop(x128, cond, lw, lb, 1e-5, 0.3, 9, None)[0]]))
+    cases.append(("adain_up_drop bwd", lambda: list(K.adain_up_drop_bwd(gu, x128, cond, lw, lb, st0))))
+    s2w, s2d = K.pack_conv3x3_weights((torch.randn(128, 64, 3, 3, generator=g) * 0.05).to(cuda))
+    xs2, ys2 = bf(3, 48, 48, 64), bf(3, 24, 24, 128)
+    cases.append(("stride-2 fprop", lambda: [K.conv3x3_s2(xs2, s2w, torch.zeros(128, device=cuda), 0.2, 128)]))
+    cases.append(("stride-2 dgrad", lambda: [K.conv3x3_s2_dgrad(ys2, s2d, 64, 48, 48)]))
+    cases.append(("stride-2 wgrad", lambda: list(K.conv3x3_s2_wgrad(xs2, ys2))))
+    img = (torch.rand(3, 3, 96, 96, generator=g) * 2 - 1).to(cuda)
+    w1 = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).to(cuda)
+    cases.append(("K=27 fprop", lambda: [K.conv_first(img, w1, torch.zeros(64, device=cuda))]))
+    cases.append(("K=27 wgrad", lambda: list(K.conv_first_wgrad(img, bf(3, 96, 96, 64) * 0 + 1))))
+    for name, fn in cases:
+        first = [t.clone() for t in fn() if t is not None]
+        torch.cuda.synchronize()
+        for rep in range(12):
+            n = (8 + 7 * rep) << 20
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    noise_dst[:n].copy_(noise_src[:n], non_blocking=True)
+            out = [t for t in fn() if t is not None]
+            for a, b in zip(first, out):
+                assert torch.equal(a, b), f"{name}: run {rep} differs from the first"
+        torch.cuda.synchronize()
