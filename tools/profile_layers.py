@@ -7,6 +7,8 @@ from weather_unet_b200 import _ops as K
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = torch.device("cuda:0")
 cases = [("dconv_up1.0", 128, 64, 64, 256), ("dconv_down2.2", 128, 0, 128, 128), ("dconv_up3.0", 512, 256, 256, 64)]
+if len(sys.argv) > 2:  # restrict to the named layers
+    cases = [c for c in cases if c[0] in sys.argv[2:]]
 work = []
 for name, c0, c1, cout, h in cases:
     s0 = torch.randn(B, h, h, c0, device=dev).to(torch.bfloat16)

@@ -11,7 +11,9 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint64, c_u
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwu_b200.so")
+# WU_B200_LIB: developer hook for A/B measurements of experimental builds (tools/pipe_stats.sh); the
+# product always loads the in-tree library
+LIB_PATH = os.environ.get("WU_B200_LIB") or os.path.join(_HERE, "lib", "libwu_b200.so")
 
 P, I, F, U64, SZ = c_void_p, c_int, c_float, c_uint64, c_size_t
 

@@ -22,6 +22,27 @@
 
 namespace wu {
 
+// Debug build only (-DWU_PIPE_STATS, tools/pipe_stats.sh): cycles the single MMA-issuing thread and
+// the TMA producer thread spend waiting on each barrier class, summed over all CTAs.  Not compiled
+// into the product library.
+#ifdef WU_PIPE_STATS
+__device__ unsigned long long g_pipe_stats[16];
+#define WU_STAT_DECL(n) long long _st[n] = {}
+#define WU_STAT_WAIT(slot, ...)        \
+  do {                                  \
+    const long long _t0 = clock64();    \
+    __VA_ARGS__;                        \
+    _st[slot] += clock64() - _t0;       \
+  } while (0)
+#define WU_STAT_FLUSH(base, n) \
+  for (int _i = 0; _i < (n); ++_i) atomicAdd(&g_pipe_stats[(base) + _i], (unsigned long long)_st[_i])
+#else
+#define WU_STAT_DECL(n)
+#define WU_STAT_WAIT(slot, ...) __VA_ARGS__
+#define WU_STAT_FLUSH(base, n)
+#endif
+
+
 // ------------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ------------------------------------------------------------------------------------------------
@@ -469,6 +490,10 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
       // ------------------------------------------------------------ TMA producer
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      WU_STAT_DECL(3);
+#ifdef WU_PIPE_STATS
+      const long long _p0 = clock64();
+#endif
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int b, h0, w0, n0;
         decode(tile, b, h0, w0, n0);
@@ -476,7 +501,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
           for (int s = 0; s < 3; ++s) {
             {
               const int wl = w0 + s - 1;
-              mbar_wait(emptyA(sa), pa ^ 1u);
+              WU_STAT_WAIT(1, mbar_wait(emptyA(sa), pa ^ 1u));
               mbar_arrive_expect_tx(fullA(sa), Cfg::kATx);
               if (cb < p.c0_blocks)
                 tma_load_4d(a_base + sa * Cfg::kABytes, &tmA0, fullA(sa), cb * 64, wl, h0 - 1, b);
@@ -486,7 +511,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
               if (++sa == SA) { sa = 0; pa ^= 1u; }
             }
             for (int r = 0; r < 3; ++r) {
-              mbar_wait(emptyB(sb), pb ^ 1u);
+              WU_STAT_WAIT(2, mbar_wait(emptyB(sb), pb ^ 1u));
               mbar_arrive_expect_tx(fullB(sb), Cfg::kBBytes);
               tma_load_2d(b_base + sb * Cfg::kBBytes, &tmB, fullB(sb),
                           ((r * 3 + s) * p.ctot_blocks + cb) * 64, n0);
@@ -495,6 +520,10 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
         }
       }
+#ifdef WU_PIPE_STATS
+      _st[0] = clock64() - _p0;
+#endif
+      WU_STAT_FLUSH(4, 3);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -508,18 +537,22 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
+      WU_STAT_DECL(4);
+#ifdef WU_PIPE_STATS
+      const long long _m0 = clock64();
+#endif
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u);
+        WU_STAT_WAIT(1, mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (T * BN);
         for (int cb = 0; cb < p.ctot_blocks; ++cb) {
           for (int s = 0; s < 3; ++s) {
-            mbar_wait(fullA(sa), pa);
+            WU_STAT_WAIT(2, mbar_wait(fullA(sa), pa));
             tc_fence_after();
             const uint64_t adesc_s = adesc0 + (uint64_t)((sa * Cfg::kABytes) >> 4);
             for (int r = 0; r < 3; ++r) {
-              mbar_wait(fullB(sb), pb);
+              WU_STAT_WAIT(3, mbar_wait(fullB(sb), pb));
               tc_fence_after();
               const uint64_t bdesc_s = bdesc0 + (uint64_t)((sb * Cfg::kBBytes) >> 4);
               const uint64_t adesc_r = adesc_s + (uint64_t)((r * RP) >> 4);
@@ -542,6 +575,10 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
         umma_commit(tfull_bar(buf));
       }
+#ifdef WU_PIPE_STATS
+      _st[0] = clock64() - _m0;
+#endif
+      WU_STAT_FLUSH(0, 4);
     }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
@@ -1026,6 +1063,10 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)(nc * Cfg::kCopyBytes + Cfg::kBBytes);
+      WU_STAT_DECL(2);
+#ifdef WU_PIPE_STATS
+      const long long _p0 = clock64();
+#endif
       for (int pt = pt_begin; pt < pt_end; ++pt) {
         int m = pt;
         const int tw = m % p.tiles_w;
@@ -1033,7 +1074,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
         const int th = m % p.tiles_h;
         const int b = m / p.tiles_h;
         const int w0 = tw * 8, h0 = th * 8;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
+        WU_STAT_WAIT(1, mbar_wait(empty_bar(stage), phase ^ 1u));
         const uint32_t fb = full_bar(stage);
         mbar_arrive_expect_tx(fb, tx);
         const uint32_t a_dst = base + stage * Cfg::kStageBytes;
@@ -1055,10 +1096,18 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
           phase ^= 1u;
         }
       }
+#ifdef WU_PIPE_STATS
+      _st[0] = clock64() - _p0;
+#endif
+      WU_STAT_FLUSH(12, 2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
+      WU_STAT_DECL(2);
+#ifdef WU_PIPE_STATS
+      const long long _m0 = clock64();
+#endif
       const int npair = (nc + 1) >> 1;
       const int nblocks = nc + npair;
       // One thread issues every MMA, so its instruction count per MMA is what paces the tensor
@@ -1084,7 +1133,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
       // FULL: every copy slot of the CTA is in use (nc == NC) -> no per-MMA liveness tests
       auto issue_stage = [&](auto full_tag, int pt) {
         constexpr bool FULL = decltype(full_tag)::value;
-        mbar_wait(full_bar(stage), phase);
+        WU_STAT_WAIT(1, mbar_wait(full_bar(stage), phase));
         tc_fence_after();
         const uint64_t soff = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
         const uint32_t acc = pt != pt_begin ? 1u : 0u;
@@ -1121,6 +1170,10 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
       }
       (void)nblocks;
       umma_commit(tfull_bar);
+#ifdef WU_PIPE_STATS
+      _st[0] = clock64() - _m0;
+#endif
+      WU_STAT_FLUSH(8, 2);
     }
   } else {
     const int q = warp & 3;
@@ -1433,6 +1486,17 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // C ABI
 // ------------------------------------------------------------------------------------------------
 using namespace wu;
+
+#ifdef WU_PIPE_STATS
+extern "C" int wu_debug_pipe_stats(unsigned long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, g_pipe_stats, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_pipe_stats, z, sizeof(z));
+  }
+  return WU_OK;
+}
+#endif
 
 extern "C" int wu_pack_conv3x3_weights(const float* w, int cout, int cin, void* w_fprop,
                                        void* w_dgrad, wu_stream_t stream) {
