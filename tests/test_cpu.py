@@ -289,3 +289,58 @@ def test_adam_tables_layout():
     assert chunks[3:] == [(1, 0, t) for t in range(24)]
     with pytest.raises(ValueError):
         optim.build_tables([dict(p=1, g=2, m=3, v=4, n=9 * 8 * 64, wf=5, wd=6, cout=8, cin=64)])
+
+
+def test_script_compat_shims(tmp_path):
+    """the torch-2.x / torchrun shims for the reference's scripts (compat.py):
+    iterator.next(), pickled-module loading, rank-aware loaders that partition the data, and the
+    trainer's iteration loop (t_cls_train.py:387-437) driving a step function."""
+    import torch
+    import torch.nn as nn
+    from torch.utils.data import TensorDataset, WeightedRandomSampler
+    from weather_unet_b200 import compat
+
+    compat.install_torch2_patches()
+    ds = TensorDataset(torch.arange(40).float().view(40, 1), torch.arange(40) % 5)
+    it = iter(compat.make_loader(ds, 4, shuffle=False, world=1, rank=0))
+    assert it.next()[0].shape == (4, 1)  # t_cls_train.py:218 idiom
+    # pickled module (t_cls_train.py:172): plain torch.load works again after the patch, and load_module
+    p = str(tmp_path / "est.pt")
+    torch.save(nn.Linear(3, 5), p)
+    assert isinstance(torch.load(p), nn.Linear) and isinstance(compat.load_module(p), nn.Linear)
+    # rank-aware loaders: the ranks' batches partition the epoch, per-rank batch size kept
+    seen = []
+    for r in range(2):
+        ld = compat.make_loader(ds, 4, shuffle=True, world=2, rank=r, seed=3)
+        compat.set_epoch(ld, 1)
+        xs = torch.cat([b[0].view(-1) for b in ld])
+        assert len(ld) == 5 and all(b[0].shape[0] == 4 for b in ld)
+        seen.append(set(xs.tolist()))
+    assert seen[0].isdisjoint(seen[1]) and len(seen[0] | seen[1]) == 40
+    # a weighted sampler's stream (ImbalancedDatasetSampler's role) is sharded, same stream per rank
+    ws = WeightedRandomSampler(torch.ones(40), 40, replacement=True)
+    a = list(compat.ShardedSampler(ws, 0, 2, seed=5))
+    b = list(compat.ShardedSampler(ws, 1, 2, seed=5))
+    torch.manual_seed(5)
+    full = list(iter(ws))
+    assert a == full[0::2] and b == full[1::2]
+    # the iteration loop: label preparation and call order
+    calls = []
+
+    def step(images, c_real, c_target):
+        calls.append((images.shape[0], c_real.clone(), c_target.clone()))
+        return {"d_loss": torch.tensor(0.0)}
+
+    saves = []
+    n = compat.train_epochs(step, compat.make_loader(ds, 8, shuffle=False, world=1, rank=0),
+                            compat.make_loader(ds, 8, shuffle=False, world=1, rank=0), 5, "cpu", epochs=2,
+                            batch_size=8, save_per_step=4, on_save=lambda e, s: saves.append((e, s)))
+    assert n == 10 and len(calls) == 10 and saves == [(0, 4), (1, 8)]
+    assert calls[0][1].shape == (8, 5) and torch.equal(calls[0][1].argmax(1), torch.arange(8) % 5)
+    est = lambda x: torch.softmax(torch.zeros(x.shape[0], 5), 1)
+    calls.clear()
+    compat.train_epochs(step, compat.make_loader(ds, 8, shuffle=False, world=1, rank=0),
+                        compat.make_loader(ds, 8, shuffle=False, world=1, rank=0), 5, "cpu",
+                        supervised=False, estimator=est)
+    assert torch.allclose(calls[0][2], torch.full((8, 5), 0.2))
+    torch.load = torch.load._wu_orig  # leave the process as we found it
