@@ -43,13 +43,45 @@ class _RoundGradBF16(torch.autograd.Function):
         return g.to(torch.bfloat16).to(g.dtype)
 
 
+class _RoundValueBF16(torch.autograd.Function):
+    """bf16-rounded value, gradient passed through unrounded."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _flags(q):
+    """emulate_bf16 may be a bool (all / nothing) or a subset of {"w", "a", "g"}: round the
+    convolution Weights, the stored Activations, the activation Gradients (tools/
+    grad_error_attribution.py separates their contributions)."""
+    if q is True:
+        return frozenset("wag")
+    if not q:
+        return frozenset()
+    return frozenset(q)
+
+
 def _q(x, on):
-    return _RoundBF16.apply(x) if on else x
+    f = _flags(on)
+    if "a" in f and "g" in f:
+        return _RoundBF16.apply(x)
+    if "a" in f:
+        return _RoundValueBF16.apply(x)
+    if "g" in f:
+        return _RoundGradBF16.apply(x)
+    return x
 
 
 def _qw(w, on):
     """bf16-rounded weight in the forward/data-gradient, fp32 master weight receives the gradient."""
-    return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach() if on else w
+    if on is True or (on and "w" in _flags(on)):
+        return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()
+    return w
 
 
 def double_conv(sd, name, x, q=False, q_first=True, tap=None):
@@ -58,8 +90,8 @@ def double_conv(sd, name, x, q=False, q_first=True, tap=None):
     q_first=False keeps the first convolution's weights in fp32 (the K=27 image layer does).
     tap: optional callable(name_suffix, tensor) -> tensor applied to both activations."""
     tap = tap or (lambda k, v: v)
-    x = _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.0.weight"], q and q_first), sd[f"{name}.0.bias"],
-                           padding=1)), q)
+    x = _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.0.weight"], q if q_first else False),
+                           sd[f"{name}.0.bias"], padding=1)), q)
     x = tap(f"{name}.a", x)
     x = _q(F.relu(F.conv2d(x, _qw(sd[f"{name}.2.weight"], q), sd[f"{name}.2.bias"], padding=1)), q)
     return tap(f"{name}.b", x)
@@ -131,7 +163,7 @@ def forward(sd, x, c, train=False, masks=None, p=P_DROP, collect=None, emulate_b
                                         ("adain2", "dconv_up2", conv2),
                                         ("adain1", "dconv_up1", conv1))):
         z = adain(sd, ad, h, c)
-        h = upsample(_RoundGradBF16.apply(z) if q else z)
+        h = upsample(_RoundGradBF16.apply(z) if "g" in _flags(q) else z)
         h, m = dropout(h, masks[i], train, p)
         h = tap(f"u{3 - i}", _q(h, q))
         if collect is not None:
