@@ -63,6 +63,16 @@ int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1, int c1, i
                            const void* relu_mask_src, void* dst, int cout, int B, int H, int W,
                            wu_stream_t stream);
 
+/* Convolution + ReLU that also emits AdaIN's statistics of its own output (utils.py:34-39 on the
+ * tensor cunet.py:59,66,73 hands to AdaIN): stats fp32 [Bout][chunks][cout][2] = (sum, sum of squares)
+ * of the STORED bf16 values per 64-pixel chunk, chunks = wu_conv3x3_stats_chunks(cout, H, W) (0 when
+ * the shape has no fused variant: cout must be 128 or a multiple of 256).  Feed it to
+ * wu_adain_style_fwd_n instead of running wu_adain_stats over the tensor again. */
+int wu_conv3x3_stats_chunks(int cout, int H, int W);
+int wu_conv3x3_fprop_stats(const void* src0, int c0, const void* src1, int c1, int src1_bcast,
+                           const void* w_packed, const float* bias, void* dst, float* stats, int cout,
+                           int B, int H, int W, wu_stream_t stream);
+
 /* The generator's last two layers in one kernel (cunet.py:78-82): dst = relu(conv3x3(src) + bias)
  * with 64 output channels (dconv_up1.2, kept for the backward pass) and, from the same registers,
  *   y[b,o,h,w] = tanh(last_b[o] + sum_c last_w[o][c] * dst[b,h,w,c])       (conv_last + Tanh)
@@ -131,6 +141,10 @@ int wu_adain_stats(const void* x, float* partial, int B, int HW, int C, wu_strea
 int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb, const float* partial,
                        float* mean, float* rstd, float* ystd, float* scale, float* shift, int B,
                        int C, int nc, int HW, float eps, int x_bcast, wu_stream_t stream);
+/* Same with an explicit chunk count (statistics produced by wu_conv3x3_fprop_stats). */
+int wu_adain_style_fwd_n(const float* cond, const float* lw, const float* lb, const float* partial,
+                         float* mean, float* rstd, float* ystd, float* scale, float* shift, int B,
+                         int C, int nc, int HW, int nchunk, float eps, int x_bcast, wu_stream_t stream);
 /* Step 3 (cunet.py:59-61): u[b,Y,X,c] = keep * bilinear_x2(x*scale+shift)[b,Y,X,c] / (1-p).
  * Dropout: p_drop == 0 -> none; else if mask != NULL it is a uint8 NHWC [B][2h][2w][C] keep mask;
  * else keep bits come from a Philox4x32-7 stream keyed by (seed, 8-channel vector index): 15 bits

@@ -387,3 +387,34 @@ def test_standalone_blocks(cuda):
     assert rel(ya, ra) < 6e-3
     with pytest.raises(RuntimeError, match="forward-only"):
         blk(x.requires_grad_(True))
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 32, 32, 256, 512), (3, 24, 40, 128, 256), (2, 48, 40, 128, 128),
+                                            (1, 40, 24, 64, 128), (2, 16, 16, 512, 512)])
+def test_conv3x3_fused_adain_stats(cuda, B, H, W, cin, cout):
+    """wu_conv3x3_fprop_stats: the convolution output is bit-identical to wu_conv3x3_fprop, and the
+    (sum, sum of squares) it emits fold to the statistics wu_adain_stats computes from the stored
+    tensor (utils.py:34-39), including ragged sizes whose tiles hang over the image edge."""
+    from weather_unet_b200 import _ops as K
+    from weather_unet_b200._lib import call, ptr, query, stream
+    g = torch.Generator().manual_seed(B * H + cout)
+    x = torch.randn(B, H, W, cin, generator=g).to(cuda).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).to(cuda)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(cuda)
+    wf, _ = K.pack_conv3x3_weights(w)
+    ref = K.conv3x3(x, None, wf, bias, True, None, cout)
+    dst, sums = K.conv3x3_stats(x, None, wf, bias, cout)
+    assert sums is not None and sums.shape[0] == B and sums.shape[2:] == (cout, 2)
+    assert torch.equal(dst, ref)
+    tot = sums.double().sum(dim=1)  # (B, cout, 2)
+    xf = dst.float().double().reshape(B, H * W, cout)
+    assert torch.allclose(tot[..., 0], xf.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(tot[..., 1], (xf * xf).sum(1), rtol=1e-5, atol=1e-3)
+    # and through the AdaIN site: same scale / shift as the separate statistics pass
+    cond = torch.randn(B, 5, generator=g).to(cuda)
+    lw, lb = (torch.randn(4 * cout, 5, generator=g) * 0.3).to(cuda), torch.zeros(4 * cout, device=cuda)
+    u1, st1 = K.adain_up_drop(dst, cond, lw, lb, 1e-5, 0.0, 0, None)
+    u2, st2 = K.adain_up_drop(dst, cond, lw, lb, 1e-5, 0.0, 0, None, stats=sums)
+    assert torch.allclose(st1.mean, st2.mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(st1.rstd, st2.rstd, rtol=1e-4)
+    assert ((u1.float() - u2.float()).abs().max() <= 2e-2 * u1.float().abs().max()).item()

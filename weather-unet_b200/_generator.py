@@ -99,9 +99,14 @@ class _CUNetFn(torch.autograd.Function):
         def wf(name):
             return packed.get(name, P[name])[0]
 
-        def block(src0, src1, name):
+        def block(src0, src1, name, stats=False):
+            """r_double_conv (nets.py:18-24).  stats: the second convolution also emits AdaIN's
+            sums of its output (the tensor goes to an AdaIN site next, cunet.py:59,66,73)."""
             cout = P[f"{name}.0.weight"].shape[0]
             a = K.conv3x3(src0, src1, wf(f"{name}.0.weight"), P[f"{name}.0.bias"], True, None, cout)
+            if stats:
+                b, sums = K.conv3x3_stats(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], cout)
+                return a, b, sums
             b = K.conv3x3(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], True, None, cout)
             return a, b
 
@@ -113,16 +118,16 @@ class _CUNetFn(torch.autograd.Function):
         conv2, p2 = K.conv3x3_pool(d2a, wf("dconv_down2.2.weight"), P["dconv_down2.2.bias"], 128)
         d3a, conv3 = block(p2, None, "dconv_down3")
         p3 = K.maxpool2(conv3)
-        d4a, x4 = block(p3, None, "dconv_down4")
+        d4a, x4, sums4 = block(p3, None, "dconv_down4", stats=True)
         # decoder (cunet.py:59-78)
         u3, st3 = K.adain_up_drop(x4, c, P["adain3.l1.weight"], P["adain3.l1.bias"], eps[0], p_drop,
-                                  seed, masks[0], epoch=epoch)
-        up3a, up3b = block(u3, conv3, "dconv_up3")
+                                  seed, masks[0], epoch=epoch, stats=sums4)
+        up3a, up3b, sums3 = block(u3, conv3, "dconv_up3", stats=True)
         u2, st2 = K.adain_up_drop(up3b, c, P["adain2.l1.weight"], P["adain2.l1.bias"], eps[1], p_drop,
-                                  seed + 1, masks[1], epoch=epoch)
-        up2a, up2b = block(u2, conv2, "dconv_up2")
+                                  seed + 1, masks[1], epoch=epoch, stats=sums3)
+        up2a, up2b, sums2 = block(u2, conv2, "dconv_up2", stats=True)
         u1, st1 = K.adain_up_drop(up2b, c, P["adain1.l1.weight"], P["adain1.l1.bias"], eps[2], p_drop,
-                                  seed + 2, masks[2], epoch=epoch)
+                                  seed + 2, masks[2], epoch=epoch, stats=sums2)
         # last block: its second convolution also applies conv_last + tanh from registers (cunet.py:78-82)
         up1a = K.conv3x3(u1, conv1, wf("dconv_up1.0.weight"), P["dconv_up1.0.bias"], True, None, 64)
         up1b, y = K.conv3x3_last(up1a, wf("dconv_up1.2.weight"), P["dconv_up1.2.bias"],
@@ -264,26 +269,29 @@ def transfer_forward(module, x1, c, masks, seed, epoch=None):
     def wf(name):
         return packed.get(name, P[name])[0]
 
-    def block(src0, src1, name, bcast=False):
+    def block(src0, src1, name, bcast=False, stats=True):
+        """-> (output, AdaIN sums of the output or None)"""
         cout = P[f"{name}.0.weight"].shape[0]
         a = K.conv3x3(src0, src1, wf(f"{name}.0.weight"), P[f"{name}.0.bias"], True, None, cout,
                       src1_bcast=bcast)
-        return K.conv3x3(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], True, None, cout)
+        if not stats:
+            return K.conv3x3(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], True, None, cout), None
+        return K.conv3x3_stats(a, None, wf(f"{name}.2.weight"), P[f"{name}.2.bias"], cout)
 
     a1 = K.conv_first(x1, P["dconv_down1.0.weight"], P["dconv_down1.0.bias"])
     conv1, p1 = K.conv3x3_pool(a1, wf("dconv_down1.2.weight"), P["dconv_down1.2.bias"], 64)
     d2a = K.conv3x3(p1, None, wf("dconv_down2.0.weight"), P["dconv_down2.0.bias"], True, None, 128)
     conv2, p2 = K.conv3x3_pool(d2a, wf("dconv_down2.2.weight"), P["dconv_down2.2.bias"], 128)
-    conv3 = block(p2, None, "dconv_down3")
-    x4 = block(K.maxpool2(conv3), None, "dconv_down4")
+    conv3, _ = block(p2, None, "dconv_down3", stats=False)
+    x4, sums = block(K.maxpool2(conv3), None, "dconv_down4")
     u3, _ = K.adain_up_drop(x4, c, P["adain3.l1.weight"], P["adain3.l1.bias"], module.adain3.eps,
-                            p_drop, seed, masks[0], x_bcast=True, epoch=epoch)
-    h = block(u3, conv3, "dconv_up3", bcast=True)
+                            p_drop, seed, masks[0], x_bcast=True, epoch=epoch, stats=sums)
+    h, sums = block(u3, conv3, "dconv_up3", bcast=True)
     u2, _ = K.adain_up_drop(h, c, P["adain2.l1.weight"], P["adain2.l1.bias"], module.adain2.eps,
-                            p_drop, seed + 1, masks[1], epoch=epoch)
-    h = block(u2, conv2, "dconv_up2", bcast=True)
+                            p_drop, seed + 1, masks[1], epoch=epoch, stats=sums)
+    h, sums = block(u2, conv2, "dconv_up2", bcast=True)
     u1, _ = K.adain_up_drop(h, c, P["adain1.l1.weight"], P["adain1.l1.bias"], module.adain1.eps,
-                            p_drop, seed + 2, masks[2], epoch=epoch)
+                            p_drop, seed + 2, masks[2], epoch=epoch, stats=sums)
     a = K.conv3x3(u1, conv1, wf("dconv_up1.0.weight"), P["dconv_up1.0.bias"], True, None, 64,
                   src1_bcast=True)
     return K.conv3x3_last(a, wf("dconv_up1.2.weight"), P["dconv_up1.2.bias"], P["conv_last.weight"],

@@ -26,6 +26,8 @@ SIGNATURES = {
     "wu_pack_conv3x3_weights": (I, [P, I, I, P, P, P]),
     "wu_conv3x3_fprop": (I, [P, I, P, I, P, P, I, P, P, I, I, I, I, P]),
     "wu_conv3x3_fprop_bcast": (I, [P, I, P, I, I, P, P, I, P, P, I, I, I, I, P]),
+    "wu_conv3x3_stats_chunks": (I, [I, I, I]),
+    "wu_conv3x3_fprop_stats": (I, [P, I, P, I, I, P, P, P, P, I, I, I, I, P]),
     "wu_conv3x3_fprop_last": (I, [P, I, P, P, P, P, P, P, I, I, I, P]),
     "wu_conv3x3_fprop_pool": (I, [P, I, P, P, P, P, I, I, I, I, P]),
     "wu_conv3x3_wgrad_workspace_bytes": (SZ, [I, I, I, I, I]),
@@ -42,6 +44,7 @@ SIGNATURES = {
     "wu_adain_stats": (I, [P, P, I, I, I, P]),
     "wu_adain_style_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "wu_adain_up_drop_fwd_epoch": (I, [P, P, P, P, P, I, I, I, I, F, U64, P, P, I, P]),
+    "wu_adain_style_fwd_n": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P]),
     "wu_adain_apply": (I, [P, P, P, P, I, I, I, P]),
     "wu_adain_up_drop_fwd": (I, [P, P, P, P, P, I, I, I, I, F, U64, P, I, P]),
     "wu_adain_bwd_chunks": (I, [I, I, I]),

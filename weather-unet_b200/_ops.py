@@ -41,6 +41,22 @@ def conv3x3(src0, src1, w_packed, bias, relu, mask, cout, src1_bcast=False):
     return dst
 
 
+def conv3x3_stats(src0, src1, w_packed, bias, cout, src1_bcast=False):
+    """conv3x3 + ReLU that also returns AdaIN's (sum, sum of squares) partials of its output
+    (wu_conv3x3_fprop_stats): -> (dst, stats (B, chunks, cout, 2) fp32), or (dst, None) when the shape
+    has no fused variant (the caller then runs wu_adain_stats)."""
+    B, H, W, c0 = src0.shape
+    chunks = query("wu_conv3x3_stats_chunks", cout, H, W)
+    if chunks <= 0:
+        return conv3x3(src0, src1, w_packed, bias, True, None, cout, src1_bcast=src1_bcast), None
+    c1 = 0 if src1 is None else src1.shape[3]
+    dst = _act(B, H, W, cout, src0)
+    stats = torch.empty((B, chunks, cout, 2), dtype=torch.float32, device=src0.device)
+    call("wu_conv3x3_fprop_stats", ptr(src0), c0, ptr(src1), c1, int(src1_bcast), ptr(w_packed),
+         ptr(bias), ptr(dst), ptr(stats), cout, B, H, W, stream())
+    return dst, stats
+
+
 def conv3x3_last(src, w_packed, bias, last_w, last_b):
     """dconv_up1.2 + conv_last + tanh in one kernel (wu_conv3x3_fprop_last):
     -> (relu(conv3x3(src)) NHWC bf16 (B,H,W,64), tanh(conv1x1) fp32 NCHW (B,3,H,W))."""
@@ -142,23 +158,28 @@ class AdaINState:
     __slots__ = ("mean", "rstd", "ystd", "scale", "shift", "seed", "mask", "p", "bits")
 
 
-def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False, epoch=None):
+def adain_up_drop(x, cond, lw, lb, eps, p_drop, seed, mask, x_bcast=False, epoch=None, stats=None):
     """AdaIN(x, cond) -> bilinear x2 (align_corners) -> dropout.  x (B,h,w,C) -> (B,2h,2w,C).
     x_bcast: x has batch 1 and serves all cond.shape[0] conditions.
-    epoch: optional device int32 scalar, the draw counter of wu_adain_up_drop_fwd_epoch."""
+    epoch: optional device int32 scalar, the draw counter of wu_adain_up_drop_fwd_epoch.
+    stats: the (sum, sum of squares) partials of x when the producing convolution already made them
+    (conv3x3_stats); otherwise one pass over x computes them."""
     Bx, h, w, C = x.shape
     B = cond.shape[0] if x_bcast else Bx
     nc = cond.shape[1]
-    nchunk = query("wu_adain_stats_chunks", h * w)
     dev = x.device
-    partial = torch.empty((Bx, nchunk, C, 2), dtype=torch.float32, device=dev)
-    call("wu_adain_stats", ptr(x), ptr(partial), Bx, h * w, C, stream())
+    if stats is not None:
+        partial, nchunk = stats, stats.shape[1]
+    else:
+        nchunk = query("wu_adain_stats_chunks", h * w)
+        partial = torch.empty((Bx, nchunk, C, 2), dtype=torch.float32, device=dev)
+        call("wu_adain_stats", ptr(x), ptr(partial), Bx, h * w, C, stream())
     st = AdaINState()
     buf = torch.empty((5, B, C), dtype=torch.float32, device=dev)
     st.mean, st.rstd, st.ystd, st.scale, st.shift = buf[0], buf[1], buf[2], buf[3], buf[4]
     st.seed, st.mask, st.p = int(seed), mask, float(p_drop)
-    call("wu_adain_style_fwd", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.mean), ptr(st.rstd),
-         ptr(st.ystd), ptr(st.scale), ptr(st.shift), B, C, nc, h * w, float(eps), int(x_bcast),
+    call("wu_adain_style_fwd_n", ptr(cond), ptr(lw), ptr(lb), ptr(partial), ptr(st.mean), ptr(st.rstd),
+         ptr(st.ystd), ptr(st.scale), ptr(st.shift), B, C, nc, h * w, nchunk, float(eps), int(x_bcast),
          stream())
     u = _act(B, 2 * h, 2 * w, C, x)
     st.bits = (torch.empty((B, 2 * h, 2 * w, C // 8), dtype=torch.uint8, device=dev)

@@ -58,7 +58,32 @@ struct ConvParams {
   int b1_mul;                 // 1, or 0 when source 1 has batch 1 and is shared by every image
   const float* bias;          // [cout] or null
   const __nv_bfloat16* mask;  // NHWC [B][H][W][cout] or null: dst = mask > 0 ? dst : 0
+  // STATS instantiation: per-(image, 64-pixel half tile, channel) sums of the stored bf16 output
+  // and of its square, [B][stats_chunks][cout][2] fp32 — AdaIN's statistics (utils.py:34-39) without
+  // another pass over the tensor
+  float* stats;
+  int stats_chunks;
 };
+
+// Sum and sum of squares of one channel over 64 pixel rows of a staged [128 px][64 ch] bf16 tile
+// (128-byte swizzle: 16-byte chunk k of row r sits at chunk position k ^ (r & 7)).  Thread et owns
+// channel et & 63 and pixel rows (et >> 6) * 64 ... + 63; `valid(r)` excludes rows outside the image.
+template <typename Valid>
+__device__ __forceinline__ void staged_tile_stats(const uint8_t* stile, int et, Valid valid, float& s1,
+                                                  float& s2) {
+  const int c = et & 63, r0 = (et >> 6) * 64;
+  const int kc = c >> 3, off = (c & 7) * 2;
+  s1 = 0.f;
+  s2 = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < 64; ++i) {
+    const int r = r0 + i;
+    const uint16_t raw = *reinterpret_cast<const uint16_t*>(stile + r * 128 + ((kc ^ (r & 7)) << 4) + off);
+    const float v = valid(r) ? __uint_as_float((uint32_t)raw << 16) : 0.f;
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+  }
+}
 
 template <int BN>
 struct ConvCfg {
@@ -161,7 +186,7 @@ __device__ __forceinline__ void epilogue_half_r(uint32_t (&v)[32], const float* 
   }
 }
 
-template <int BN>
+template <int BN, bool STATS>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                      const __grid_constant__ CUtensorMap tmA1,
@@ -328,6 +353,19 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           tma_store_4d(&tmD, sb, cbase, t.w0, t.h0, t.b);
           tma_store_commit();
         }
+        if (STATS) {
+          // the staged tile is rewritten only after the next-but-one chunk's barrier, which every
+          // thread reaches after these reads
+          const int et = threadIdx.x - 64;
+          float s1, s2;
+          staged_tile_stats(smem + (sb - base), et, [&](int r) {
+            return (t.h0 + (r >> p.log2_bw) < p.H) && (t.w0 + (r & (p.bw - 1)) < p.W); }, s1, s2);
+          const int mt = tile / p.n_tiles;  // (b, th, tw) linear
+          const int in_img = mt - t.b * p.tiles_h * p.tiles_w;
+          float* o = p.stats + (((size_t)t.b * p.stats_chunks + in_img * 2 + (et >> 6)) * p.cout + cbase +
+                                (et & 63)) * 2;
+          *reinterpret_cast<float2*>(o) = make_float2(s1, s2);
+        }
       }
     }
     if (issuer) tma_store_wait_all<0>();
@@ -338,18 +376,18 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN>
+template <int BN, bool STATS = false>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
                        const CUtensorMap& dm, const ConvParams& p, cudaStream_t st) {
   using Cfg = ConvCfg<BN>;
   static bool attr_done = false;  // benign race: idempotent
   if (!attr_done) {
-    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel<BN>,
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel<BN, STATS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv3x3_igemm_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
+  conv3x3_igemm_kernel<BN, STATS><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_kernel");
   return WU_OK;
 }
@@ -383,6 +421,9 @@ struct ConvParams2 {
   // POOL instantiation (dconv_down1.2 / dconv_down2.2): nn.MaxPool2d(2) (cunet.py:46,49) of the tile,
   // taken from the staged bf16 tile before it leaves shared memory: pool_dst NHWC [B][H/2][W/2][cout]
   __nv_bfloat16* pool_dst;
+  // STATS instantiation (dconv_up2.2): AdaIN sums of the stored output, see ConvParams::stats
+  float* stats;
+  int stats_chunks;
 };
 
 // (A variant that loads ONE 10-pixel-wide TMA box per channel block and reaches the three column
@@ -410,7 +451,7 @@ struct ConvCfg2 {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int T, bool LAST, bool POOL>
+template <int BN, int T, bool LAST, bool POOL, bool STATS>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
                         const __grid_constant__ CUtensorMap tmA1,
@@ -702,6 +743,16 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
             if (h0 + 16 * t < p.H) tma_store_4d(&tmD, sbuf, cbase, w0, h0 + 16 * t, b);
             tma_store_commit();
           }
+          if (STATS) {
+            float s1, s2;
+            staged_tile_stats(smem + (sbuf - base), et, [&](int r) {
+              return (h0 + 16 * t + (r >> 3) < p.H) && (w0 + (r & 7) < p.W); }, s1, s2);
+            const int mt = tile / p.n_tiles;  // (b, th, tw) linear
+            const int in_img = mt - b * p.tiles_h * p.tiles_w;
+            float* o = p.stats + (((size_t)b * p.stats_chunks + (in_img * T + t) * 2 + (et >> 6)) * p.cout +
+                                  cbase + (et & 63)) * 2;
+            *reinterpret_cast<float2*>(o) = make_float2(s1, s2);
+          }
           if (POOL) {
             // 2x2 max over the staged [16 x 8 px][64 ch] tile -> 8 x 4 pooled pixels; a task is one
             // 16-byte chunk of one pooled pixel (256 tasks, two per thread).  Values are post-ReLU
@@ -741,18 +792,18 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN, int T, bool LAST = false, bool POOL = false>
+template <int BN, int T, bool LAST = false, bool POOL = false, bool STATS = false>
 static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
                         const CUtensorMap& dm, const ConvParams2& p, cudaStream_t st) {
   using Cfg = ConvCfg2<BN, T>;
   static bool attr_done = false;
   if (!attr_done) {
-    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST, POOL>,
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, T, LAST, POOL, STATS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv3x3_igemm_v2_kernel<BN, T, LAST, POOL>
+  conv3x3_igemm_v2_kernel<BN, T, LAST, POOL, STATS>
       <<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_v2_kernel");
   return WU_OK;
@@ -1519,10 +1570,51 @@ extern "C" int wu_conv3x3_fprop(const void* src0, int c0, const void* src1, int 
                                 B, H, W, stream);
 }
 
+// Number of 64-pixel statistics chunks per image the STATS instantiations write (0: unsupported)
+static int fprop_stats_chunks(int cout, int H, int W) {
+  if (cout != 128 && cout % 256 != 0) return 0;
+  if (cout == 128) {  // v2 <128, 2>: super-tiles of 32 rows x 8 columns, two 16-row tiles each
+    return ((W + 7) / 8) * ((H + 31) / 32) * 2 * 2;
+  }
+  int bw, bh;  // v1 <256>: one 128-pixel box per tile
+  pick_box(H, W, 128, &bw, &bh);
+  return ((W + bw - 1) / bw) * ((H + bh - 1) / bh) * 2;
+}
+
+extern "C" int wu_conv3x3_stats_chunks(int cout, int H, int W) {
+  if (cout <= 0 || H <= 0 || W <= 0 || conv_impl() != 0) return 0;
+  return fprop_stats_chunks(cout, H, W);
+}
+
+static int conv3x3_fprop_impl(const void* src0, int c0, const void* src1, int c1, int src1_bcast,
+                              const void* w_packed, const float* bias, int relu,
+                              const void* relu_mask_src, void* dst, int cout, int B, int H, int W,
+                              float* stats, wu_stream_t stream);
+
 extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1, int c1,
                                       int src1_bcast, const void* w_packed, const float* bias,
                                       int relu, const void* relu_mask_src, void* dst, int cout,
                                       int B, int H, int W, wu_stream_t stream) {
+  return conv3x3_fprop_impl(src0, c0, src1, c1, src1_bcast, w_packed, bias, relu, relu_mask_src, dst,
+                            cout, B, H, W, nullptr, stream);
+}
+
+extern "C" int wu_conv3x3_fprop_stats(const void* src0, int c0, const void* src1, int c1,
+                                      int src1_bcast, const void* w_packed, const float* bias,
+                                      void* dst, float* stats, int cout, int B, int H, int W,
+                                      wu_stream_t stream) {
+  WU_REQUIRE(stats != nullptr, "wu_conv3x3_fprop_stats: null stats pointer");
+  WU_REQUIRE(wu_conv3x3_stats_chunks(cout, H, W) > 0,
+             "wu_conv3x3_fprop_stats: cout=%d must be 128 or a multiple of 256", cout);
+  WU_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 7) == 0, "wu_conv3x3_fprop_stats: stats unaligned");
+  return conv3x3_fprop_impl(src0, c0, src1, c1, src1_bcast, w_packed, bias, 1, nullptr, dst, cout, B, H,
+                            W, stats, stream);
+}
+
+static int conv3x3_fprop_impl(const void* src0, int c0, const void* src1, int c1, int src1_bcast,
+                              const void* w_packed, const float* bias, int relu,
+                              const void* relu_mask_src, void* dst, int cout, int B, int H, int W,
+                              float* stats, wu_stream_t stream) {
   WU_REQUIRE(src0 && w_packed && dst, "wu_conv3x3_fprop: null pointer");
   WU_REQUIRE(B > 0 && H > 0 && W > 0, "wu_conv3x3_fprop: bad shape B=%d H=%d W=%d", B, H, W);
   WU_REQUIRE(c0 > 0 && c0 % 64 == 0, "wu_conv3x3_fprop: c0=%d must be a positive multiple of 64", c0);
@@ -1554,6 +1646,8 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     q.last_w = q.last_b = nullptr;
     q.last_y = nullptr;
     q.pool_dst = nullptr;
+    q.stats = stats;
+    q.stats_chunks = stats ? fprop_stats_chunks(cout, H, W) : 0;
     CUtensorMap a0, a1, bm, dm;
     int rc;
     if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, bw, 16 * T + 2)) != WU_OK) return rc;
@@ -1566,6 +1660,10 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
     if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * (c0 + c1), bn)) != WU_OK) return rc;
     if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, 8, 16)) != WU_OK) return rc;
     cudaStream_t st2 = (cudaStream_t)stream;
+    if (stats != nullptr) {
+      WU_REQUIRE(bn == 128, "wu_conv3x3_fprop_stats: internal: v2 statistics need N = 128");
+      return launch_conv2<128, 2, false, false, true>(a0, a1, bm, dm, q, st2);
+    }
     switch (bn) {
       case 64: return launch_conv2<64, 4>(a0, a1, bm, dm, q, st2);
       case 128: return launch_conv2<128, 2>(a0, a1, bm, dm, q, st2);
@@ -1591,6 +1689,8 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
   p.b1_mul = src1_bcast ? 0 : 1;
   p.bias = bias;
   p.mask = (const __nv_bfloat16*)relu_mask_src;
+  p.stats = stats;
+  p.stats_chunks = stats ? fprop_stats_chunks(cout, H, W) : 0;
   CUtensorMap a0, a1, bm, dm;
   int rc;
   if ((rc = make_act_tmap(&a0, src0, B, H, W, c0, c0, p.bw, p.bh)) != WU_OK) return rc;
@@ -1603,6 +1703,10 @@ extern "C" int wu_conv3x3_fprop_bcast(const void* src0, int c0, const void* src1
   if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * (c0 + c1), bn)) != WU_OK) return rc;
   if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, p.bw, p.bh)) != WU_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (stats != nullptr) {
+    WU_REQUIRE(bn == 256, "wu_conv3x3_fprop_stats: internal: v1 statistics need N = 256");
+    return launch_conv<256, true>(a0, a1, bm, dm, p, st);
+  }
   switch (bn) {
     case 64: return launch_conv<64>(a0, a1, bm, dm, p, st);
     case 128: return launch_conv<128>(a0, a1, bm, dm, p, st);
@@ -1637,6 +1741,8 @@ extern "C" int wu_conv3x3_fprop_last(const void* src, int cin, const void* w_pac
   q.last_b = last_b;
   q.last_y = y;
   q.pool_dst = nullptr;
+  q.stats = nullptr;
+  q.stats_chunks = 0;
   CUtensorMap a0, bm, dm;
   int rc;
   if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;
@@ -1673,6 +1779,8 @@ extern "C" int wu_conv3x3_fprop_pool(const void* src, int cin, const void* w_pac
   q.last_w = q.last_b = nullptr;
   q.last_y = nullptr;
   q.pool_dst = (__nv_bfloat16*)pool_dst;
+  q.stats = nullptr;
+  q.stats_chunks = 0;
   CUtensorMap a0, bm, dm;
   int rc;
   if ((rc = make_act_tmap(&a0, src, B, H, W, cin, cin, 8, 16 * T + 2)) != WU_OK) return rc;

@@ -1247,18 +1247,25 @@ extern "C" int wu_adain_stats(const void* x, float* partial, int B, int HW, int 
   WU_CHECK_LAUNCH("adain_stats_kernel");
   return WU_OK;
 }
-extern "C" int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb,
+extern "C" int wu_adain_style_fwd_n(const float* cond, const float* lw, const float* lb,
                                   const float* partial, float* mean, float* rstd, float* ystd,
                                   float* scale, float* shift, int B, int C, int nc, int HW,
-                                  float eps, int x_bcast, wu_stream_t stream) {
+                                  int nchunk, float eps, int x_bcast, wu_stream_t stream) {
   WU_REQUIRE(cond && lw && lb && partial && mean && rstd && ystd && scale && shift,
              "wu_adain_style_fwd: null pointer");
-  WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0, "wu_adain_style_fwd: bad shape");
+  WU_REQUIRE(B > 0 && C > 0 && nc > 0 && HW > 0 && nchunk > 0, "wu_adain_style_fwd: bad shape");
   adain_style_fwd_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       cond, lw, lb, partial, mean, rstd, ystd, scale, shift, B, C, nc, HW,
-      wu_adain_stats_chunks(HW), eps, x_bcast ? 0 : 1);
+      nchunk, eps, x_bcast ? 0 : 1);
   WU_CHECK_LAUNCH("adain_style_fwd_kernel");
   return WU_OK;
+}
+extern "C" int wu_adain_style_fwd(const float* cond, const float* lw, const float* lb,
+                                  const float* partial, float* mean, float* rstd, float* ystd,
+                                  float* scale, float* shift, int B, int C, int nc, int HW, float eps,
+                                  int x_bcast, wu_stream_t stream) {
+  return wu_adain_style_fwd_n(cond, lw, lb, partial, mean, rstd, ystd, scale, shift, B, C, nc, HW,
+                              wu_adain_stats_chunks(HW), eps, x_bcast, stream);
 }
 extern "C" int wu_adain_up_drop_fwd(const void* x, const float* scale, const float* shift, void* u,
                                     uint8_t* keep_bits, int B, int h, int w, int C, float p_drop,
