@@ -17,7 +17,10 @@ try:
 except Exception as e: print('no line', e)")"
 }
 run graph ""
-if [ "$2" != quick ]; then
+if [ "$2" = ctas ]; then  # how many SMs may NCCL take away from the persistent convolution kernels?
+  NCCL_MAX_CTAS=2 run graph_ctas2 ""
+  NCCL_MAX_CTAS=8 run graph_ctas8 ""
+elif [ "$2" != quick ]; then
   run noallreduce "--no-allreduce"
   run eager "--no-graph"
 fi
