@@ -49,11 +49,14 @@ for name, c0, c1, cout, d in layers:
     f = stats(lambda: K.conv3x3(s0, s1, wf, bias, True, None, cout))
     w = stats(lambda: K.conv3x3_wgrad(s0, s1, dy))
     line = f"{name:8s} {c0 + c1:4d}->{cout:3d} @{h:3d}^2 | fprop"
-    if f[0]:
+    if cout % 256 == 0:  # v1 kernel: one barrier per (A, B) stage
+        line += (f" v1 MMA thread waits: tmem-empty {pct(f[1], f[0])} full {pct(f[2], f[0])}"
+                 f" | producer waits: empty {pct(f[5], f[4])}")
+    elif f[0]:
         line += (f" MMA thread waits: tmem-empty {pct(f[1], f[0])} fullA {pct(f[2], f[0])} fullB {pct(f[3], f[0])}"
                  f" | producer waits: emptyA {pct(f[5], f[4])} emptyB {pct(f[6], f[4])}")
     else:
-        line += " (v1 kernel: not instrumented)"
+        line += " (?)"
     line += f" | wgrad MMA waits full {pct(w[9], w[8])}, producer waits empty {pct(w[13], w[12])}"
     print(line, flush=True)
     if not c1 and f[0]:

@@ -242,12 +242,16 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      WU_STAT_DECL(2);
+#ifdef WU_PIPE_STATS
+      const long long _p0 = clock64();
+#endif
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<BN>(p, tile);
         for (int tap = 0; tap < 9; ++tap) {
           const int r = tap / 3, s = tap - 3 * r;
           for (int cb = 0; cb < p.ctot_blocks; ++cb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            WU_STAT_WAIT(1, mbar_wait(empty_bar(stage), phase ^ 1u));
             const uint32_t fb = full_bar(stage);
             mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
             const uint32_t a_dst = base + stage * Cfg::kStageBytes;
@@ -265,21 +269,29 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
         }
       }
+#ifdef WU_PIPE_STATS
+      _st[0] = clock64() - _p0;
+#endif
+      WU_STAT_FLUSH(4, 2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer (one thread)
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      WU_STAT_DECL(3);
+#ifdef WU_PIPE_STATS
+      const long long _m0 = clock64();
+#endif
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u);
+        WU_STAT_WAIT(1, mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          WU_STAT_WAIT(2, mbar_wait(full_bar(stage), phase));
           tc_fence_after();
           const uint32_t a_addr = base + stage * Cfg::kStageBytes;
           const uint32_t b_addr = a_addr + Cfg::kABytes;
@@ -297,6 +309,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
         umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
       }
+#ifdef WU_PIPE_STATS
+      _st[0] = clock64() - _m0;
+#endif
+      WU_STAT_FLUSH(0, 3);
     }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
@@ -389,6 +405,267 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   conv3x3_igemm_kernel<BN, STATS><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
   WU_CHECK_LAUNCH("conv3x3_igemm_kernel");
+  return WU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// N = 256 on CTA PAIRS (tcgen05 cta_group::2, M = 256): conv3x3_igemm_pair_kernel
+// ------------------------------------------------------------------------------------------------
+// Why (profiles/r02_pipeline_experiments.txt): the single-CTA N = 256 kernel above moves 48 KiB per
+// 512 MMA cycles from L2 into every SM (a 16 KiB pixel tile + the whole 32 KiB weight tile), and its
+// MMA-issuing thread waits 15-26 % of the time for those bytes.  In a pair each CTA keeps its own 128
+// pixels but only HALF of the weight tile (128 of the 256 rows of B): 32 KiB per 512 cycles and SM,
+// stages of 32 KiB instead of 48 (six instead of four in flight), 64 instead of 96 B/clk of operand
+// reads.  Same tiling, same accumulation order per output element as the single-CTA kernel, hence
+// bit-identical results.
+// Pair protocol (validated in round 1 on the N = 64 kernel, where it did not pay because that shape is
+// bound by the operand read rate, not by delivery):
+//   * cluster (2,1,1); pair-tile = two M-tiles (128 pixels each) x one N-tile; CTA r owns M-tile 2m + r;
+//   * "full" barriers live in the leader (CTA 0): it posts expect_tx for the bytes of BOTH CTAs and both
+//     producers' cp.async.bulk.tensor ... .cta_group::2 loads complete on it;
+//   * "empty" and "accumulator full" barriers exist in both CTAs, signalled by the leader's
+//     tcgen05.commit.cta_group::2 ... multicast;
+//   * "accumulator drained" lives in the leader (256 arrivals: both CTAs' epilogue threads).
+struct ConvPairCfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = 128 * 128;  // 128 pixels x 64 ch x 2 B
+  static constexpr int kBBytes = 128 * 128;  // this CTA's 128 of the 256 weight rows x 64 k x 2 B
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = 2 * 16384;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
+  static constexpr uint32_t kTmemCols = 512;  // two accumulator buffers of 256 columns
+};
+
+template <bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv3x3_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0,
+                          const __grid_constant__ CUtensorMap tmA1,
+                          const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmD, const ConvParams p) {
+  using Cfg = ConvPairCfg;
+  constexpr int S = Cfg::kStages, BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t staging_base = base + S * Cfg::kStageBytes;
+  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_tiles = p.batch * p.tiles_h * p.tiles_w;
+  const int num_pairs_total = ((m_tiles + 1) >> 1) * p.n_tiles;  // the last M pair may have one live half
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 256);  // both CTAs' epilogue threads (used in the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int kblocks = 9 * p.ctot_blocks;
+
+  // M-tile of this CTA inside pair-tile `pt`; the dead half of an odd tail re-does the last tile
+  auto decode = [&](int pt, int& mtile, int& b, int& h0, int& w0, int& n0, bool& live) {
+    const int nt = pt % p.n_tiles;
+    const int mp = pt / p.n_tiles;
+    mtile = 2 * mp + (int)rank;
+    live = mtile < m_tiles;
+    if (!live) mtile = m_tiles - 1;
+    const int tw = mtile % p.tiles_w;
+    const int mt = mtile / p.tiles_w;
+    const int th = mt % p.tiles_h;
+    b = mt / p.tiles_h;
+    h0 = th * p.bh;
+    w0 = tw * p.bw;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pair; pt < num_pairs_total; pt += npairs) {
+        int mtile, b, h0, w0, n0;
+        bool live;
+        decode(pt, mtile, b, h0, w0, n0, live);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, s = tap - 3 * r;
+          for (int cb = 0; cb < p.ctot_blocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            const uint32_t fb = cluster_map(full_bar(stage), 0);
+            const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+            const uint32_t b_dst = a_dst + Cfg::kABytes;
+            if (cb < p.c0_blocks)
+              tma_load_4d_pair(a_dst, &tmA0, fb, cb * 64, w0 + s - 1, h0 + r - 1, b);
+            else
+              tma_load_4d_pair(a_dst, &tmA1, fb, (cb - p.c0_blocks) * 64, w0 + s - 1, h0 + r - 1,
+                               b * p.b1_mul);
+            tma_load_2d_pair(b_dst, &tmB, fb, (tap * p.ctot_blocks + cb) * 64, n0 + 128 * (int)rank);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader, one thread)
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = pair; pt < num_pairs_total; pt += npairs, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 16) per 64-channel block
+            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(empty_bar(stage));  // frees the slot in BOTH CTAs once these MMAs retire
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_pair(tfull_bar(buf));  // accumulator complete -> both epilogues
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5, both CTAs)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // pixel within the tile == TMEM lane
+    const bool issuer = (threadIdx.x == 64);
+    const int ph = row >> p.log2_bw;
+    const int pw = row & (p.bw - 1);
+    const uint32_t tempty_leader[2] = {cluster_map(tempty_bar(0), 0), cluster_map(tempty_bar(1), 0)};
+    uint32_t store_count = 0;
+    int it = 0;
+    for (int pt = pair; pt < num_pairs_total; pt += npairs, ++it) {
+      const int buf = it & 1;
+      int mtile, b, h0, w0, n0;
+      bool live;
+      decode(pt, mtile, b, h0, w0, n0, live);
+      const int h = h0 + ph, w = w0 + pw;
+      const bool inb = live && (h < p.H) && (w < p.W);
+      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 64; ++chunk) {
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + chunk * 64;
+        tmem_ld_32x32(taddr, v0);
+        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_wait();
+        if (chunk == BN / 64 - 1) {  // this thread has drained its part of the accumulator
+          tc_fence_before();
+          mbar_arrive_cluster(tempty_leader[buf]);
+        }
+        const int cbase = n0 + chunk * 64;
+        const float* bptr = p.bias != nullptr ? p.bias + cbase : nullptr;
+        const uint4* mptr = nullptr;
+        if (p.mask != nullptr && inb)
+          mptr = reinterpret_cast<const uint4*>(
+              p.mask + ((size_t)(b * p.H + h) * p.W + w) * p.cout + cbase);
+        uint32_t pk0[16], pk1[16];
+        epilogue_half(v0, bptr, p.relu, mptr, pk0);
+        epilogue_half(v1, bptr ? bptr + 32 : nullptr, p.relu, mptr ? mptr + 4 : nullptr, pk1);
+        const uint32_t sb = staging_base + (store_count & 1u) * 16384u;
+        ++store_count;
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint8_t* srow = smem + (sb - base) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) =
+              make_uint4(pk0[4 * j], pk0[4 * j + 1], pk0[4 * j + 2], pk0[4 * j + 3]);
+          *reinterpret_cast<uint4*>(srow + (((j + 4) ^ (row & 7)) << 4)) =
+              make_uint4(pk1[4 * j], pk1[4 * j + 1], pk1[4 * j + 2], pk1[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (issuer) {
+          if (live) tma_store_4d(&tmD, sb, cbase, w0, h0, b);
+          tma_store_commit();
+        }
+        if (STATS) {
+          if (live) {
+            const int et = threadIdx.x - 64;
+            float s1, s2;
+            staged_tile_stats(smem + (sb - base), et, [&](int r) {
+              return (h0 + (r >> p.log2_bw) < p.H) && (w0 + (r & (p.bw - 1)) < p.W); }, s1, s2);
+            const int in_img = mtile - b * p.tiles_h * p.tiles_w;
+            float* o = p.stats + (((size_t)b * p.stats_chunks + in_img * 2 + (et >> 6)) * p.cout + cbase +
+                                  (et & 63)) * 2;
+            *reinterpret_cast<float2*>(o) = make_float2(s1, s2);
+          }
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody frees tensor memory (or exits) while the pair still uses it
+  if (warp == 2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+}
+
+template <bool STATS>
+static int launch_conv_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bm,
+                            const CUtensorMap& dm, const ConvParams& p, cudaStream_t st) {
+  using Cfg = ConvPairCfg;
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    WU_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_pair_kernel<STATS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int m_tiles = p.batch * p.tiles_h * p.tiles_w;
+  const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
+  const int max_pairs = num_sms() / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  conv3x3_igemm_pair_kernel<STATS><<<grid, 192, Cfg::kSmemBytes, st>>>(a0, a1, bm, dm, p);
+  WU_CHECK_LAUNCH("conv3x3_igemm_pair_kernel");
   return WU_OK;
 }
 
@@ -819,6 +1096,19 @@ static int conv_impl() {
     if (v < 0 || v > 2) v = 0;
   }
   return v;
+}
+
+// WU_CONV_PAIR=0 keeps the single-CTA N = 256 kernel (A/B measurements); default: CTA pairs
+#ifndef WU_PAIR_DEFAULT
+#define WU_PAIR_DEFAULT 1
+#endif
+static bool conv_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WU_CONV_PAIR");
+    v = e ? (atoi(e) != 0) : WU_PAIR_DEFAULT;
+  }
+  return v != 0;
 }
 
 static int ilog2(int v) {
@@ -1700,9 +1990,13 @@ static int conv3x3_fprop_impl(const void* src0, int c0, const void* src1, int c1
   } else {
     a1 = a0;
   }
-  if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * (c0 + c1), bn)) != WU_OK) return rc;
+  const bool pair = bn == 256 && conv_pair();  // CTA pairs (cta_group::2): half a weight tile per CTA
+  if ((rc = make_mat_tmap(&bm, w_packed, cout, 9 * (c0 + c1), pair ? 128 : bn)) != WU_OK) return rc;
   if ((rc = make_act_tmap(&dm, dst, B, H, W, cout, cout, p.bw, p.bh)) != WU_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pair)
+    return stats != nullptr ? launch_conv_pair<true>(a0, a1, bm, dm, p, st)
+                            : launch_conv_pair<false>(a0, a1, bm, dm, p, st);
   if (stats != nullptr) {
     WU_REQUIRE(bn == 256, "wu_conv3x3_fprop_stats: internal: v1 statistics need N = 256");
     return launch_conv<256, true>(a0, a1, bm, dm, p, st);
