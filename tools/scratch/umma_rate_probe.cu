@@ -98,6 +98,82 @@ rate_kernel(long long* cycles, int iters, int a_tiles, int b_tiles, int tma, con
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// CTA-pair variant: M = 256 across two CTAs, each supplying its own 128 rows of A and HALF of B.
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+rate_pair_kernel(long long* cycles, int iters, int a_tiles, int b_tiles) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const uint32_t raw = smem_u32(sm);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* s = sm + (base - raw);
+  constexpr int kBTile = (N / 2) * 128;  // this CTA's half: N/2 rows x 64 k x 2 B
+  const uint32_t a_base = base, b_base = base + a_tiles * kATile;
+  const uint32_t done = b_base + b_tiles * kBTile, slot = done + 16;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool leader = cluster_ctarank() == 0;
+  for (int i = tid; i < (a_tiles * kATile + b_tiles * kBTile) / 16; i += 128)
+    reinterpret_cast<uint4*>(s)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair<512>(slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(s + (slot - base));
+  if (leader && tid == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(256, N, 0, 0);
+    const uint64_t ad0 = umma_smem_desc_sw128(a_base, 16, 1024);
+    const uint64_t bd0 = umma_smem_desc_sw128(b_base, 16, 1024);
+    int ai = 0, bi = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint64_t ad = ad0 + (uint64_t)((ai * kATile) >> 4);
+      const uint64_t bd = bd0 + (uint64_t)((bi * kBTile) >> 4);
+#pragma unroll
+      for (int t = 0; t < 512 / N / 2; ++t) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_pair(tmem + t * N, ad + (uint64_t)((k * 32) >> 4), bd + (uint64_t)((k * 32) >> 4), idesc,
+                         (it | k) ? 1u : 0u);
+      }
+      if (++ai == a_tiles) ai = 0;
+      if (++bi == b_tiles) bi = 0;
+    }
+    umma_commit_pair(done);
+    mbar_wait(done, 0);
+    cycles[blockIdx.x >> 1] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+template <int N>
+static void run_pair(int a_tiles, int b_tiles, long long* dcyc) {
+  const int iters = 4000;
+  const int smem = a_tiles * kATile + b_tiles * (N / 2) * 128 + 64 + 1024;
+  cudaFuncSetAttribute(rate_pair_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int grid = 148;
+  for (int rep = 0; rep < 2; ++rep) {
+    rate_pair_kernel<N><<<grid, 128, smem>>>(dcyc, iters, a_tiles, b_tiles);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("pair N=%d: %s\n", N, cudaGetErrorString(e)); exit(1); }
+  }
+  std::vector<long long> h(grid / 2);
+  cudaMemcpy(h.data(), dcyc, (grid / 2) * sizeof(long long), cudaMemcpyDeviceToHost);
+  double sum = 0;
+  for (auto v : h) sum += (double)v;
+  const double per_group = 4.0 * (512 / N / 2);
+  const double cyc = sum / (grid / 2) / iters / per_group;
+  printf("CTA pair M=256 N=%3d K-major a_tiles=%d b_tiles=%d: %.1f cycles per MMA (ideal %d) -> %.1f %% of the "
+         "tensor pipe\n", N, a_tiles, b_tiles, cyc, N / 2, 100.0 * (N / 2) / cyc);
+}
+
 template <int N, int MN>
 static void run(int a_tiles, int b_tiles, int tma, const uint8_t* gsrc, long long* dcyc) {
   const int iters = 4000;
@@ -138,6 +214,9 @@ int main() {
     run<128, 1>(4, 4, tma, gsrc, dcyc);
     run<256, 1>(4, 3, tma, gsrc, dcyc);
   }
+  run_pair<64>(4, 4, dcyc);
+  run_pair<128>(4, 4, dcyc);
+  run_pair<256>(4, 3, dcyc);
   printf("RESULT done\n");
   return 0;
 }
