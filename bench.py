@@ -484,6 +484,11 @@ def run_ours(args):
                   ("dconv_up2.2", 128, 0, 128, 2), ("dconv_up1.2", 64, 0, 64, 1)]
         per_layer, tot = {}, {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
         for name, c0, c1, cout, d in layers:
+            # every layer is "a kernel timed alone" against the burst peak: a short idle gap before
+            # each one, so that the layers at the end of the list are not measured on a board the
+            # earlier ones have driven into its power cap (dconv_up1.2 read 10 % low in round 1)
+            torch.cuda.synchronize()
+            time.sleep(0.4)
             h = S // d
             s0 = torch.randn(B, h, h, c0, device=dev).to(torch.bfloat16)
             s1 = torch.randn(B, h, h, c1, device=dev).to(torch.bfloat16) if c1 else None
