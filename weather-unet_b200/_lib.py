@@ -134,6 +134,23 @@ def query(name, *args):
     return getattr(load(), name)(*args)
 
 
+def on_tensor_device(fn):
+    """Decorator for autograd.Function.forward / backward: run under the CUDA device of the first
+    CUDA tensor argument.  The caller's (or the autograd engine thread's) current device need not be
+    the one that holds the data, and kernels, TMA descriptors and the stream all follow the current
+    device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args):
+        t = next((a for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if t is None:
+            return fn(ctx, *args)
+        with torch.cuda.device(t.device):
+            return fn(ctx, *args)
+    return wrapper
+
+
 _checked_devices = set()
 
 

@@ -7,7 +7,7 @@ bf16 tensors of shape (B, H, W, C).
 import torch
 
 from . import _lib
-from ._lib import call, ptr, query, stream
+from ._lib import call, on_tensor_device, ptr, query, stream
 
 BF16 = torch.bfloat16
 
@@ -234,6 +234,7 @@ class _BiasAct(torch.autograd.Function):
     memory), with a one-pass backward (masked gradient + deterministic bias gradient)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, bias, slope):
         B, C, H, W = x.shape
         call("wu_bias_act_fwd", ptr(x), ptr(bias), float(slope), B * H * W, C, stream())
@@ -243,6 +244,7 @@ class _BiasAct(torch.autograd.Function):
         return x
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, gy):
         (y,) = ctx.saved_tensors
         B, C, H, W = y.shape
@@ -275,6 +277,7 @@ class _DiscStem(torch.autograd.Function):
     spectral_norm hook's output), so autograd continues into weight_orig / sigma on the torch side."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, w0, b0, w1, b1, slope):
         B, _, H, W = x.shape
         dev = x.device
@@ -290,6 +293,7 @@ class _DiscStem(torch.autograd.Function):
         return c1.permute(0, 3, 1, 2)  # NCHW-shaped view of NHWC memory == channels_last
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, gy):
         x, h1, c1, w0c, w1c = ctx.saved_tensors
         B, _, H, W = x.shape
@@ -378,6 +382,7 @@ class _DiscBlock(torch.autograd.Function):
     their gradients flow back into the spectral-norm graph (weight_orig, sigma) on the torch side."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, w0, b0, w1, b1, slope, packed):
         xn = x.permute(0, 2, 3, 1)  # NHWC view of channels_last memory
         if xn.dtype != BF16 or not xn.is_contiguous():
@@ -396,6 +401,7 @@ class _DiscBlock(torch.autograd.Function):
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, gy):
         xn, h, y, w0d, w1d = ctx.saved_tensors
         B, H, W, cin = xn.shape
@@ -441,6 +447,7 @@ class _L1PerSample(torch.autograd.Function):
     """d[s] = mean |a[s] - b[s]| per sample in one pass (and one pass backward, gradient w.r.t. `a`)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, a, b):
         B = a.shape[0]
         n = a[0].numel()
@@ -452,6 +459,7 @@ class _L1PerSample(torch.autograd.Function):
         return d
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, gd):
         a, b = ctx.saved_tensors
         ga = torch.empty_like(a)

@@ -8,7 +8,7 @@ import struct
 
 import torch
 
-from ._lib import call, query, stream
+from ._lib import call, on_tensor_device, query, stream
 
 
 _REC = "<QQQQQQQQQQQQQQii"  # one SnTensor record of csrc/wu_spectral.cu (14 pointers, rows, cols)
@@ -119,6 +119,7 @@ class FusedSpectralNorm:
 class _SNAll(torch.autograd.Function):
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, sn, training, *ws):
         dev = ws[0].device
         st = sn._static_chunks(dev)
@@ -164,6 +165,7 @@ class _SNAll(torch.autograd.Function):
         return tuple(outs) + tuple(extra)
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, *grads):
         grads = grads[:ctx.n]  # the packed bf16 copies are not differentiable
         sn, ws = ctx.sn, ctx.saved_tensors
