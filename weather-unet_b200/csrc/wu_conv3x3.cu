@@ -1320,6 +1320,7 @@ struct WgradParams2 {
   int cout, cin_total;
   float* partial;       // [splits][9*cin_total][cout]
   float* bias_partial;  // [4*splits][cout] column sums of dY (bias gradient), or null
+  int merge;            // every CTA's NC copies come from one source tensor: one 5-D TMA box per stage
 };
 
 template <int BN, int NC>
@@ -1343,6 +1344,8 @@ template <int BN, int NC>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
                         const __grid_constant__ CUtensorMap tmX1,
+                        const __grid_constant__ CUtensorMap tmX0m,
+                        const __grid_constant__ CUtensorMap tmX1m,
                         const __grid_constant__ CUtensorMap tmY, const WgradParams2 p) {
   using Cfg = WgradCfg2<BN, NC>;
   constexpr int S = Cfg::kStages;
@@ -1378,6 +1381,8 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX0);
     tma_prefetch_desc(&tmX1);
+    tma_prefetch_desc(&tmX0m);
+    tma_prefetch_desc(&tmX1m);
     tma_prefetch_desc(&tmY);
   }
   // Bias gradient db[co] = sum_px dY[px][co]: the dY tiles pass through this CTA's shared memory
@@ -1404,37 +1409,65 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)(nc * Cfg::kCopyBytes + Cfg::kBBytes);
+      const bool merged = p.merge != 0 && nc == NC;
       WU_STAT_DECL(2);
 #ifdef WU_PIPE_STATS
       const long long _p0 = clock64();
 #endif
+      // This ONE thread feeds the whole CTA: every instruction it executes per stage delays the next TMA
+      // issue, and the MMAs starve behind it (measured: adding two integer divisions per copy and stage
+      // cost the N = 64 layers 18-27 %; merging two dY boxes into one gained 4-6 %).  So everything that
+      // does not change from stage to stage is computed here, once: which tensor map, channel
+      // coordinate and column shift each copy uses, and the tile coordinates advance by increments.
+      // Global copy id g = s * ctot_blocks + cb: a CTA's copies are consecutive channel blocks of ONE
+      // column shift (the other shifts of the same blocks belong to neighbouring CTAs of the split and
+      // are fetched at about the same time: L2 hits).  When they all come from one source tensor, ONE
+      // 5-D TMA box fetches them (the copies land back to back in shared memory).
+      const CUtensorMap* cmap[NC];
+      int cch[NC], csh[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int g = g0 + (c < nc ? c : 0);
+        const int s = g / p.ctot_blocks, cb = g - s * p.ctot_blocks;
+        const bool first = cb < p.c0_blocks;
+        csh[c] = s - 1;
+        if (merged) {
+          cmap[c] = first ? &tmX0m : &tmX1m;
+          cch[c] = first ? cb : cb - p.c0_blocks;  // block coordinate of the 5-D map
+        } else {
+          cmap[c] = first ? &tmX0 : &tmX1;
+          cch[c] = (first ? cb : cb - p.c0_blocks) * 64;
+        }
+      }
+      const int ny = n0 >> 6;
+      int tw = pt_begin % p.tiles_w;
+      int th = (pt_begin / p.tiles_w) % p.tiles_h;
+      int b = pt_begin / (p.tiles_w * p.tiles_h);
       for (int pt = pt_begin; pt < pt_end; ++pt) {
-        int m = pt;
-        const int tw = m % p.tiles_w;
-        m /= p.tiles_w;
-        const int th = m % p.tiles_h;
-        const int b = m / p.tiles_h;
         const int w0 = tw * 8, h0 = th * 8;
         WU_STAT_WAIT(1, mbar_wait(empty_bar(stage), phase ^ 1u));
         const uint32_t fb = full_bar(stage);
         mbar_arrive_expect_tx(fb, tx);
         const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-        const uint32_t b_dst = a_dst + Cfg::kABytes;
-        for (int c = 0; c < nc; ++c) {
-          const int g = g0 + c;  // global copy id = cb * 3 + s: the three column shifts of a
-          const int cb = g / 3, s = g - cb * 3;  // channel block are fetched together (L2 hits)
-          if (cb < p.c0_blocks)
-            tma_load_4d(a_dst + c * Cfg::kCopyBytes, &tmX0, fb, cb * 64, w0 + s - 1, h0 - 1, b);
-          else
-            tma_load_4d(a_dst + c * Cfg::kCopyBytes, &tmX1, fb, (cb - p.c0_blocks) * 64, w0 + s - 1,
-                        h0 - 1, b);
-        }
+        if (merged) {
+          tma_load_5d(a_dst, cmap[0], fb, 0, w0 + csh[0], h0 - 1, cch[0], b);
+        } else {
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(b_dst + j * Cfg::kAtomBytes, &tmY, fb, n0 + j * 64, w0, h0, b);
+          for (int c = 0; c < NC; ++c)
+            if (c < nc) tma_load_4d(a_dst + c * Cfg::kCopyBytes, cmap[c], fb, cch[c], w0 + csh[c], h0 - 1, b);
+        }
+        // one 5-D box fetches the BN / 64 channel-block tiles of dY (they land back to back)
+        tma_load_5d(a_dst + Cfg::kABytes, &tmY, fb, 0, w0, h0, ny, b);
         if (++stage == S) {
           stage = 0;
           phase ^= 1u;
+        }
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            ++b;
+          }
         }
       }
 #ifdef WU_PIPE_STATS
@@ -1571,7 +1604,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
       }
       const bool valid = c < nc;
       const int g = g0 + (valid ? c : 0);
-      const int cb = g / 3, s = g - cb * 3;
+      const int s = g / p.ctot_blocks, cb = g - s * p.ctot_blocks;
       const int tap = r * 3 + s;
       float* out = p.partial +
                    ((size_t)z * 9 * p.cin_total + (size_t)tap * p.cin_total + cb * 64 + r64) * p.cout + n0;
@@ -1596,8 +1629,9 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX0,
 }
 
 template <int BN, int NC>
-static int launch_wgrad2(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& ym,
-                         const WgradParams2& p, int grid, cudaStream_t st) {
+static int launch_wgrad2(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& x0m,
+                         const CUtensorMap& x1m, const CUtensorMap& ym, const WgradParams2& p, int grid,
+                         cudaStream_t st) {
   using Cfg = WgradCfg2<BN, NC>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1605,7 +1639,7 @@ static int launch_wgrad2(const CUtensorMap& x0, const CUtensorMap& x1, const CUt
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  conv3x3_wgrad_v2_kernel<BN, NC><<<grid, 192, Cfg::kSmemBytes, st>>>(x0, x1, ym, p);
+  conv3x3_wgrad_v2_kernel<BN, NC><<<grid, 192, Cfg::kSmemBytes, st>>>(x0, x1, x0m, x1m, ym, p);
   WU_CHECK_LAUNCH("conv3x3_wgrad_v2_kernel");
   return WU_OK;
 }
@@ -2156,7 +2190,7 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     q.partial = reinterpret_cast<float*>(workspace);
     float* bscratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.partial_bytes);
     q.bias_partial = db != nullptr ? bscratch : nullptr;  // 4 * splits <= kBiasGradBlocks rows
-    CUtensorMap x0, x1, ym;
+    CUtensorMap x0, x1, x0m, x1m, ym;
     int rc;
     if ((rc = make_act_tmap(&x0, src0, B, H, W, c0, c0, 8, 10)) != WU_OK) return rc;
     if (c1 > 0) {
@@ -2164,12 +2198,24 @@ extern "C" int wu_conv3x3_wgrad(const void* src0, int c0, const void* src1, int 
     } else {
       x1 = x0;
     }
-    if ((rc = make_act_tmap(&ym, dy, B, H, W, cout, cout, 8, 8)) != WU_OK) return rc;
+    // groups of pl.nc copies never straddle a column shift or the two sources -> merged 5-D loads
+    q.merge = (q.ctot_blocks % pl.nc == 0 && q.c0_blocks % pl.nc == 0) ? 1 : 0;
+    x0m = x0;
+    x1m = x1;
+    if (q.merge) {
+      if ((rc = make_act_tmap_blocks(&x0m, src0, B, H, W, c0, c0, 8, 10, pl.nc)) != WU_OK) return rc;
+      if (c1 > 0) {
+        if ((rc = make_act_tmap_blocks(&x1m, src1, B, H, W, c1, c1, 8, 10, pl.nc)) != WU_OK) return rc;
+      } else {
+        x1m = x0m;
+      }
+    }
+    if ((rc = make_act_tmap_blocks(&ym, dy, B, H, W, cout, cout, 8, 8, pl.bn / 64)) != WU_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = pl.groups * pl.n_tiles * pl.splits;
-    if (pl.bn == 64 && pl.nc == 3) rc = launch_wgrad2<64, 3>(x0, x1, ym, q, grid, st);
-    else if (pl.bn == 64) rc = launch_wgrad2<64, 5>(x0, x1, ym, q, grid, st);
-    else rc = launch_wgrad2<128, 2>(x0, x1, ym, q, grid, st);
+    if (pl.bn == 64 && pl.nc == 3) rc = launch_wgrad2<64, 3>(x0, x1, x0m, x1m, ym, q, grid, st);
+    else if (pl.bn == 64) rc = launch_wgrad2<64, 5>(x0, x1, x0m, x1m, ym, q, grid, st);
+    else rc = launch_wgrad2<128, 2>(x0, x1, x0m, x1m, ym, q, grid, st);
     if (rc != WU_OK) return rc;
     if (db == nullptr) return wgrad_fold(q.partial, pl.splits, cin, cout, dw, dy, 0, nullptr, nullptr, st);
     {  // split-K fold + fold of the in-kernel column sums ([4 * splits][cout] -> db), one launch

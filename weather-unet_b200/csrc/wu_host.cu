@@ -63,6 +63,28 @@ int make_act_tmap(CUtensorMap* out, const void* ptr, int B, int H, int W, int c,
   return WU_OK;
 }
 
+int make_act_tmap_blocks(CUtensorMap* out, const void* ptr, int B, int H, int W, int c, int ctot, int bw,
+                         int bh, int nblk) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
+    return fail(WU_ERR_INVALID, "activation pointer %p not 16-byte aligned", ptr);
+  if (c % 64 != 0 || ctot % 8 != 0 || nblk < 1 || nblk > c / 64)
+    return fail(WU_ERR_INVALID, "blocked activation view: c=%d pitch=%d nblk=%d", c, ctot, nblk);
+  cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(c / 64), (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)ctot * 2, (cuuint64_t)W * ctot * 2, 128,
+                           (cuuint64_t)H * W * ctot * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)nblk, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(WU_ERR_CUDA, "cuTensorMapEncodeTiled(act5 B=%d H=%d W=%d c=%d pitch=%d box=%dx%dx%d) -> %d",
+                B, H, W, c, ctot, bw, bh, nblk, (int)r);
+  return WU_OK;
+}
+
 int make_act_tmap_strided(CUtensorMap* out, const void* ptr, int B, int Hv, int Wv, int c,
                           long long pitch_w_bytes, long long pitch_h_bytes, long long pitch_b_bytes,
                           int bw, int bh) {

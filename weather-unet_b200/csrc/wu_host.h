@@ -31,6 +31,12 @@ int fail(int code, const char* fmt, ...);
 // Builds a 4-D (C, W, H, B) tiled map with box (64, bw, bh, 1) and 128-byte swizzle.
 int make_act_tmap(CUtensorMap* out, const void* ptr, int B, int H, int W, int c, int ctot, int bw,
                   int bh);
+// The same view with the 64-channel block index as a dimension of its own: 5-D (64, W, H, c/64, B), box
+// (64, bw, bh, nblk, 1).  ONE TMA instruction then fetches the tiles of nblk consecutive channel blocks,
+// which land back to back in shared memory (bw * bh * 128 bytes each) — the layout several 4-D loads
+// would have produced.  Coordinates: (0, w, h, first block, b).
+int make_act_tmap_blocks(CUtensorMap* out, const void* ptr, int B, int H, int W, int c, int ctot, int bw,
+                         int bh, int nblk);
 // Row-major bf16 matrix [rows][cols] (cols contiguous), box (64, box_rows), 128-byte swizzle.
 int make_mat_tmap(CUtensorMap* out, const void* ptr, int rows, int cols, int box_rows);
 
