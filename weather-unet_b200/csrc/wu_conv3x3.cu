@@ -510,29 +510,35 @@ conv3x3_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer (both CTAs)
+      // One thread feeds the CTA: keep its per-stage instruction count minimal (see the weight-gradient
+      // kernel): the leader's barrier window is mapped once, the weight-tile K coordinate and the
+      // channel-block coordinate advance by increments, no division inside the stage loop.
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t full_leader = cluster_map(full_bar(0), 0);  // + 8 * stage
+      const int brow = 128 * (int)rank;
       for (int pt = pair; pt < num_pairs_total; pt += npairs) {
         int mtile, b, h0, w0, n0;
         bool live;
         decode(pt, mtile, b, h0, w0, n0, live);
-        for (int tap = 0; tap < 9; ++tap) {
-          const int r = tap / 3, s = tap - 3 * r;
-          for (int cb = 0; cb < p.ctot_blocks; ++cb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-            const uint32_t fb = cluster_map(full_bar(stage), 0);
-            const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-            const uint32_t b_dst = a_dst + Cfg::kABytes;
-            if (cb < p.c0_blocks)
-              tma_load_4d_pair(a_dst, &tmA0, fb, cb * 64, w0 + s - 1, h0 + r - 1, b);
-            else
-              tma_load_4d_pair(a_dst, &tmA1, fb, (cb - p.c0_blocks) * 64, w0 + s - 1, h0 + r - 1,
-                               b * p.b1_mul);
-            tma_load_2d_pair(b_dst, &tmB, fb, (tap * p.ctot_blocks + cb) * 64, n0 + 128 * (int)rank);
-            if (++stage == S) {
-              stage = 0;
-              phase ^= 1u;
+        const int b1 = b * p.b1_mul;
+        const int nrow = n0 + brow;
+        int kcoord = 0;  // (tap * ctot_blocks + cb) * 64
+        for (int r = 0; r < 3; ++r) {
+          for (int s = 0; s < 3; ++s) {
+            const int wc = w0 + s - 1, hc = h0 + r - 1;
+            for (int cb = 0; cb < p.ctot_blocks; ++cb, kcoord += 64) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+              const uint32_t fb = full_leader + 8u * stage;
+              const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+              if (cb < p.c0_blocks) tma_load_4d_pair(a_dst, &tmA0, fb, cb * 64, wc, hc, b);
+              else tma_load_4d_pair(a_dst, &tmA1, fb, (cb - p.c0_blocks) * 64, wc, hc, b1);
+              tma_load_2d_pair(a_dst + Cfg::kABytes, &tmB, fb, kcoord, nrow);
+              if (++stage == S) {
+                stage = 0;
+                phase ^= 1u;
+              }
             }
           }
         }
