@@ -7,8 +7,15 @@
 
 A "step" is one training iteration of the reference trainer (t_cls_train.py:288-312 D update +
 :226-286 G update, supervised branch, estimator term omitted: SURVEY §8d) on one synthetic batch:
-batch 64 per GPU at 256x256 (BASELINE.json configs[1]).  Weak scaling: the per-GPU batch is fixed.
-One JSON line on stdout (rank 0).
+batch 64 per GPU at 256x256 (BASELINE.json configs[1]; `--size 512 --batch 32` = configs[4]), replayed
+from its CUDA graph (`--no-graph`: kernel by kernel).  Weak scaling: the per-GPU batch is fixed.
+One JSON line on stdout (rank 0).  Besides the contract's keys the line carries: `roofline` (dominant
+kernel, all-layer and per-layer fractions of the measured bf16 peak, the HBM-bound kernels),
+`cpu_baseline` (oracle train step + the config-1 single-image forward on the host cores),
+`gpu_comparator` (the oracle trainer through PyTorch/cuDNN on the same GPU: fp32-TF32 and bf16
+autocast), `estimator_plugged_step`, `transfer` / `transfer_dedup` (one image x 1024 signals, device
+resident and end to end with every output copied back to pinned host memory), `per_rank` (step time,
+SM clock, power of every rank).  `--no-allreduce` is an ablation for the scaling analysis only.
 """
 import argparse
 import json
