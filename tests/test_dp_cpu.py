@@ -112,3 +112,62 @@ def test_two_rank_step_matches_single_rank():
         if k.endswith("_u") or k.endswith("_v"):
             continue  # power-iteration buffers see different forward counts per shard: not compared
         assert torch.allclose(v, single[k], atol=2e-4, rtol=1e-3), f"{k}: DP(2) != single-rank"
+
+
+def test_static_grads_single_process_equal_plain_step():
+    """GDTrainStep(static_grads=True) — the bucket bookkeeping without a process group, what the
+    CUDA-graph replay relies on — gives the same parameters as the plain step, keeps every .grad at a
+    fixed address across iterations, and leaves the never-used parameter without a gradient."""
+    from weather_unet_b200.train_step import GDTrainStep
+    x, cr, ct = _data(4)
+    Ga, Da = _make(3)
+    Gb, Db = _make(3)
+    ta = GDTrainStep(Ga, Da, lr=1e-3, d_autocast=False, fused_adam=False)
+    tb = GDTrainStep(Gb, Db, lr=1e-3, d_autocast=False, fused_adam=False, static_grads=True)
+    assert tb.g_buckets is not None and not tb.g_buckets.collective and not tb.distributed
+    ptrs = None
+    for it in range(3):
+        la = ta.step(x, cr, ct)
+        lb = tb.step(x, cr, ct)
+        assert all(torch.equal(la[k], lb[k]) for k in la), it
+        now = {n: p.grad.data_ptr() for n, p in list(Gb.named_parameters()) + list(Db.named_parameters())
+               if p.grad is not None}
+        if ptrs is not None:
+            assert now == ptrs, "a gradient moved between iterations"
+        ptrs = now
+    assert Gb.unused.weight.grad is None
+    for (n, p), (_, q) in zip(list(Ga.named_parameters()) + list(Da.named_parameters()),
+                              list(Gb.named_parameters()) + list(Db.named_parameters())):
+        assert torch.equal(p, q), n
+
+
+def test_packed_weight_cache_protocol():
+    """_generator.PackedWeights: one persistent buffer pair per weight (fixed addresses), repack when
+    the master's version counter or storage changes, no repack after a writer called mark_fresh
+    (what optim.FusedAdam does after rewriting the copies itself), repack after invalidate()."""
+    from weather_unet_b200 import _generator as gen
+    calls = []
+    orig = gen.K.pack_conv3x3_weights_into
+    gen.K.pack_conv3x3_weights_into = lambda w, wf, wd: calls.append(w._version)
+    try:
+        pw = gen.PackedWeights()
+        w = torch.nn.Parameter(torch.randn(64, 128, 3, 3))
+        wf, wd = pw.get("a", w)
+        assert wf.shape == (64, 9 * 128) and wd.shape == (128, 9 * 64) and len(calls) == 1
+        assert pw.get("a", w)[0] is wf and len(calls) == 1            # unchanged master: cache hit
+        with torch.no_grad():
+            w.add_(1.0)                                               # torch optimiser step
+        assert pw.get("a", w)[0] is wf and len(calls) == 2            # same buffers, repacked
+        torch.autograd.graph.increment_version(w)                     # raw-pointer writer ...
+        pw.mark_fresh("a", w)                                         # ... that rewrote the copies itself
+        pw.get("a", w)
+        assert len(calls) == 2
+        torch.autograd.graph.increment_version(w)                     # raw-pointer writer that did not
+        pw.get("a", w)
+        assert len(calls) == 3
+        pw.invalidate()
+        assert pw.get("a", w)[1] is wd and len(calls) == 4
+        w2 = torch.nn.Parameter(torch.randn(64, 64, 3, 3))            # another shape under the same name
+        assert pw.get("a", w2)[0].shape == (64, 9 * 64) and len(calls) == 5
+    finally:
+        gen.K.pack_conv3x3_weights_into = orig
