@@ -51,6 +51,8 @@ def parse():
                     help="launch the iteration kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--no-allreduce", action="store_true",
                     help="ablation for the scaling analysis: skip the gradient all-reduces (replicas drift)")
+    ap.add_argument("--bucket-mb", type=int, default=8,
+                    help="size of the gradient all-reduce buckets (scaling analysis)")
     ap.add_argument("--no-comparator", action="store_true",
                     help="skip the PyTorch/cuDNN same-box comparator and the estimator-plugged step")
     ap.add_argument("--profiler-range", action="store_true",
@@ -315,7 +317,7 @@ def run_ours(args):
     torch.manual_seed(100)
     D = SNDisc(nc).to(dev).train()
     use_graph = not args.no_graph
-    trainer = GDTrainStep(G, D, lr=1e-4, static_grads=use_graph)
+    trainer = GDTrainStep(G, D, lr=1e-4, static_grads=use_graph, bucket_bytes=args.bucket_mb << 20)
     if args.no_allreduce and trainer.g_buckets is not None:
         trainer.g_buckets.collective = trainer.d_buckets.collective = False
 

@@ -127,7 +127,8 @@ class GDTrainStep:
     """
 
     def __init__(self, G, D, lr=1e-4, estimator=None, d_autocast=True, eps_con=1e-2, group=None,
-                 overlap=True, distributed=None, share_fake=False, fused_adam=None, static_grads=False):
+                 overlap=True, distributed=None, share_fake=False, fused_adam=None, static_grads=False,
+                 bucket_bytes=8 << 20):
         self.G, self.D, self.estimator = G, D, estimator
         # share_fake=True is NOT the reference's schedule: the reference runs the generator twice per
         # iteration (t_cls_train.py:302 and :242) with two independent dropout draws; sharing one
@@ -152,8 +153,10 @@ class GDTrainStep:
         if self.distributed or static_grads:
             skip = tuple(n for n, _ in G.named_parameters() if n.endswith("emb.weight"))
             coll = self.distributed and dist.is_available() and dist.is_initialized()
-            self.g_buckets = GradBuckets(G.named_parameters(), group, skip=skip, collective=coll)
-            self.d_buckets = GradBuckets(D.named_parameters(), group, collective=coll)
+            self.g_buckets = GradBuckets(G.named_parameters(), group, bucket_bytes=bucket_bytes, skip=skip,
+                                         collective=coll)
+            self.d_buckets = GradBuckets(D.named_parameters(), group, bucket_bytes=bucket_bytes,
+                                         collective=coll)
             self.d_buckets.attach_autograd_hooks()
             # the generator's backward writes its gradients straight into the buckets; the sink is
             # handed to the module only around the G update's forward (step()), so a backward
