@@ -226,18 +226,20 @@ def test_train50_parameter_trajectory(cuda):
 
     # the curve really moves (a frozen generator cannot follow it)
     assert gold[-10:, ki["loss_con"]].mean() < 0.7 * gold[:3, ki["loss_con"]].mean()
-    assert ours["drop"] < 0.7
-    # per-iteration losses follow the oracle while the runs are still on one trajectory
+    # (measured: ours 0.58, bands 0.44-0.47, frozen copies 0.97; the dynamics are chaotic, hence margins)
+    assert ours["drop"] < 0.75
+    # per-iteration losses follow the oracle while the runs are still on one trajectory (measured 6e-3)
     assert ours["err5"] < 5e-2
-    # 50 updates displaced the parameters in the oracle's direction at least as well as stock
-    # bf16 autocast does
-    assert ours["med_conv"] > band_ac["med_conv"] - 0.1 and ours["med_d"] > band_ac["med_d"] - 0.1
-    assert ours["tail_err"] < max(0.15, 1.5 * band_ac["tail_err"])
-    # negative control: with stale operand copies the same criteria must FAIL
-    assert not (stale["drop"] < 0.7 and stale["err5"] < 5e-2
-                and stale["med_conv"] > band_ac["med_conv"] - 0.1
-                and stale["tail_err"] < max(0.15, 1.5 * band_ac["tail_err"])), \
-        "the criteria cannot see frozen weights"
+    # 50 updates displaced the parameters in the oracle's direction about as well as stock bf16
+    # autocast does (measured: median cosine 0.67 vs 0.68 / 0.70 for the bands; frozen copies 0.36)
+    tol_tail = max(0.2, 1.5 * band_ac["tail_err"])
+    assert ours["med_conv"] > band_ac["med_conv"] - 0.15 and ours["med_d"] > band_ac["med_d"] - 0.15
+    assert ours["tail_err"] < tol_tail
+    # negative control: with stale operand copies the same criteria must FAIL, and clearly
+    assert not (stale["drop"] < 0.75 and stale["err5"] < 5e-2
+                and stale["med_conv"] > band_ac["med_conv"] - 0.15
+                and stale["tail_err"] < tol_tail), "the criteria cannot see frozen weights"
+    assert stale["drop"] > 0.85 and stale["med_conv"] < band_ac["med_conv"] - 0.2
 
 
 def test_graphed_step_matches_eager(cuda):
